@@ -1,0 +1,350 @@
+"""ctypes binding of ``libasq_b200.so`` (the C ABI declared in ``include/asq.h``).
+
+PyTorch is used only for device memory and streams: every compute call hands raw device
+pointers, sizes and the current CUDA stream to the library.  There is no CPU or eager fallback:
+if the library is missing, fails to load, or the tensors are not on a CUDA device, the call
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from pathlib import Path
+from typing import Optional, Tuple
+
+import torch
+
+_PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = _PKG_DIR / "libasq_b200.so"
+
+# enums of include/asq.h
+ASQ_F32, ASQ_F16, ASQ_BF16, ASQ_I32, ASQ_I8 = 0, 1, 2, 3, 4
+ACT_ROUND, ACT_SCALE, ACT_PER_TOKEN, ACT_PER_TENSOR_DYNAMIC = 0, 1, 2, 3
+DIV_RECIPROCAL, DIV_EXACT = 0, 1
+EPI_RELU = 1
+
+_DTYPE_CODE = {
+    torch.float32: ASQ_F32,
+    torch.float16: ASQ_F16,
+    torch.bfloat16: ASQ_BF16,
+    torch.int32: ASQ_I32,
+    torch.int8: ASQ_I8,
+}
+
+# every symbol include/asq.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = (
+    "asq_version",
+    "asq_last_error",
+    "asq_device_supported",
+    "asq_workspace_bytes",
+    "asq_w8a8_linear",
+    "asq_fp8_linear",
+    "asq_i8gemm_o32",
+    "asq_i8gemm_epi",
+    "asq_quantize_act",
+)
+
+_lib = None
+_lib_lock = threading.Lock()
+_launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+# How `tensor / python_scalar` is evaluated (see asq_div_mode in include/asq.h).  The default
+# reproduces the reference on its only supported device (CUDA); tests switch to DIV_EXACT to
+# compare with the CPU oracle that is pinned against the reference's Python executed on CPU.
+_default_div_mode = DIV_EXACT if os.environ.get("ASQ_DIV_MODE", "").lower() == "exact" else DIV_RECIPROCAL
+
+
+def set_div_mode(mode: int) -> int:
+    """Set the process-wide scalar-division mode; returns the previous one."""
+    global _default_div_mode
+    if mode not in (DIV_RECIPROCAL, DIV_EXACT):
+        raise ValueError("div mode must be DIV_RECIPROCAL or DIV_EXACT")
+    prev, _default_div_mode = _default_div_mode, mode
+    return prev
+
+
+def get_div_mode() -> int:
+    return _default_div_mode
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def load():
+    """Load the shared library (once) and declare the C signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m autosmoothquant_b200.build` "
+                "(there is no CPU / eager fallback for the W8A8 path)"
+            )
+        lib = ctypes.CDLL(str(LIB_PATH))
+        c_vp, c_i, c_i64, c_f, c_sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+        lib.asq_version.restype = c_i
+        lib.asq_version.argtypes = []
+        lib.asq_last_error.restype = ctypes.c_char_p
+        lib.asq_last_error.argtypes = []
+        lib.asq_device_supported.restype = c_i
+        lib.asq_device_supported.argtypes = []
+        lib.asq_workspace_bytes.restype = c_sz
+        lib.asq_workspace_bytes.argtypes = [c_i64, c_i64]
+        lib.asq_w8a8_linear.restype = c_i
+        lib.asq_w8a8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f,
+                                        c_vp, c_vp, c_i, c_vp, c_sz, c_vp]
+        lib.asq_fp8_linear.restype = c_i
+        lib.asq_fp8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f,
+                                       c_vp, c_i, c_vp, c_sz, c_vp]
+        lib.asq_i8gemm_o32.restype = c_i
+        lib.asq_i8gemm_o32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]
+        lib.asq_i8gemm_epi.restype = c_i
+        lib.asq_i8gemm_epi.argtypes = [c_vp, c_vp, c_vp, c_i, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_f, c_i, c_vp]
+        lib.asq_quantize_act.restype = c_i
+        lib.asq_quantize_act.argtypes = [c_vp, c_i, c_vp, c_vp, c_i64, c_i64, c_i, c_f, c_i, c_i, c_vp]
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = load().asq_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libasq_b200 error {rc}: {msg}")
+
+
+def _require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "autosmoothquant_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback "
+                f"(got a tensor on {t.device})"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    if dev is None:
+        raise RuntimeError("no tensor given")
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dtype}") from None
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+# ---------------------------------------------------------------- workspace
+# One scratch buffer per (device, stream): launches on a stream are ordered, so they can share it.
+# It is zero-filled once (the kernels restore their phase counters before exiting) and only grows.
+_ws_cache: dict = {}
+_ws_lock = threading.Lock()
+
+
+def _workspace(dev: torch.device, stream: int, nbytes: int) -> Tuple[int, int]:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream)
+    with _ws_lock:
+        buf = _ws_cache.get(key)
+        if buf is None or buf.numel() < nbytes + 1024:
+            size = max(nbytes + 1024, 1 << 20)
+            size = 1 << (size - 1).bit_length()  # grow geometrically
+            buf = torch.zeros(size, dtype=torch.uint8, device=dev)
+            _ws_cache[key] = buf
+    base = (buf.data_ptr() + 1023) & ~1023
+    return base, buf.numel() - (base - buf.data_ptr())
+
+
+def release_workspaces() -> None:
+    with _ws_lock:
+        _ws_cache.clear()
+
+
+# ---------------------------------------------------------------- entry points
+def w8a8_linear(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    act_mode: int,
+    quant_scale: float = 1.0,
+    dequant_scale: float = 1.0,
+    col_scale: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    row_scale_out: Optional[torch.Tensor] = None,
+    div_mode: Optional[int] = None,
+) -> torch.Tensor:
+    """Fused quantise -> INT8 GEMM -> dequant (+bias) for a 2-D ``x`` [M,K]; returns [M,N]."""
+    global _launches
+    dev = _require_cuda(x, weight, bias, col_scale, row_scale_out)
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
+    if weight.dtype != torch.int8:
+        raise TypeError(f"weight must be int8, got {weight.dtype}")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if not weight.is_contiguous():
+        raise ValueError("weight must be contiguous [N,K]")
+    for name, t in (("bias", bias), ("col_scale", col_scale), ("row_scale_out", row_scale_out)):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous float32 tensor")
+    M, K = x.shape
+    N = weight.shape[0]
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((M, N), dtype=out_dtype, device=dev)
+    if M == 0:
+        return y
+    lib = load()
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        need = lib.asq_workspace_bytes(M, K)
+        ws, ws_bytes = _workspace(dev, stream, need)
+        rc = lib.asq_w8a8_linear(
+            x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
+            M, N, K, act_mode, float(quant_scale), float(dequant_scale), _ptr(col_scale), _ptr(row_scale_out),
+            _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
+        )
+    _check(rc)
+    _launches += 1
+    return y
+
+
+def fp8_linear(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    act_mode: int,
+    in_scale: float = 1.0,
+    w_scale: float = 1.0,
+    out_dtype: Optional[torch.dtype] = None,
+    row_scale_out: Optional[torch.Tensor] = None,
+    div_mode: Optional[int] = None,
+) -> torch.Tensor:
+    """Fused quantise -> e4m3 GEMM (fp32 accumulate) -> scale (+bias); ``weight`` is float8_e4m3fn [N,K]."""
+    global _launches
+    dev = _require_cuda(x, weight, bias, row_scale_out)
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
+    if weight.dtype not in (torch.float8_e4m3fn, torch.uint8):
+        raise TypeError(f"weight must be float8_e4m3fn, got {weight.dtype}")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if not weight.is_contiguous():
+        raise ValueError("weight must be contiguous [N,K]")
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        raise TypeError("bias must be a contiguous float32 tensor")
+    M, K = x.shape
+    N = weight.shape[0]
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((M, N), dtype=out_dtype, device=dev)
+    if M == 0:
+        return y
+    lib = load()
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        need = lib.asq_workspace_bytes(M, K)
+        ws, ws_bytes = _workspace(dev, stream, need)
+        rc = lib.asq_fp8_linear(
+            x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
+            M, N, K, act_mode, float(in_scale), float(w_scale), _ptr(row_scale_out),
+            _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
+        )
+    _check(rc)
+    _launches += 1
+    return y
+
+
+def i8gemm_o32(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> None:
+    """out[M,N] (int32) = a[M,K] (int8) @ w[N,K]^T (int8), exact, in place on ``out``."""
+    global _launches
+    dev = _require_cuda(a, w, out)
+    if a.dtype != torch.int8 or w.dtype != torch.int8 or out.dtype != torch.int32:
+        raise TypeError("i8gemm_o32 expects int8, int8, int32 tensors")
+    if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1] or tuple(out.shape) != (a.shape[0], w.shape[0]):
+        raise ValueError(f"shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
+    if not (a.is_contiguous() and w.is_contiguous() and out.is_contiguous()):
+        raise ValueError("i8gemm_o32 expects contiguous tensors")
+    if a.shape[0] == 0:
+        return
+    with torch.cuda.device(dev):
+        rc = load().asq_i8gemm_o32(a.data_ptr(), w.data_ptr(), out.data_ptr(), a.shape[0], w.shape[0], a.shape[1],
+                                   _stream(dev))
+    _check(rc)
+    _launches += 1
+
+
+def i8gemm_epi(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    out: torch.Tensor,
+    alpha: float,
+    beta: float = 0.0,
+    bias: Optional[torch.Tensor] = None,
+    relu: bool = False,
+) -> None:
+    """out = convert(alpha * (a @ w^T) + beta * bias) with optional ReLU; ``out`` int8/int32/float."""
+    global _launches
+    dev = _require_cuda(a, w, out, bias)
+    if a.dtype != torch.int8 or w.dtype != torch.int8:
+        raise TypeError("i8gemm_epi expects int8 operands")
+    if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1] or tuple(out.shape) != (a.shape[0], w.shape[0]):
+        raise ValueError(f"shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
+    if not (a.is_contiguous() and w.is_contiguous() and out.is_contiguous()):
+        raise ValueError("i8gemm_epi expects contiguous tensors")
+    if bias is not None and (not bias.is_contiguous() or bias.numel() != w.shape[0]):
+        raise ValueError("bias must be a contiguous [N] tensor")
+    if a.shape[0] == 0:
+        return
+    with torch.cuda.device(dev):
+        rc = load().asq_i8gemm_epi(
+            a.data_ptr(), w.data_ptr(), _ptr(bias), _code(bias.dtype) if bias is not None else ASQ_F32,
+            out.data_ptr(), _code(out.dtype), a.shape[0], w.shape[0], a.shape[1], float(alpha), float(beta),
+            EPI_RELU if relu else 0, _stream(dev),
+        )
+    _check(rc)
+    _launches += 1
+
+
+def quantize_act(
+    x: torch.Tensor,
+    act_mode: int,
+    quant_scale: float = 1.0,
+    fp8: bool = False,
+    div_mode: Optional[int] = None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Parity tap of the fused prologue: returns (q [M,K] int8 | float8_e4m3fn, row_scale [M] or None)."""
+    global _launches
+    dev = _require_cuda(x)
+    if x.dim() != 2:
+        raise ValueError("quantize_act expects a 2-D tensor")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    M, K = x.shape
+    q = torch.empty((M, K), dtype=torch.uint8 if fp8 else torch.int8, device=dev)
+    rs = torch.empty((M,), dtype=torch.float32, device=dev) if act_mode == ACT_PER_TOKEN else None
+    if M > 0:
+        with torch.cuda.device(dev):
+            rc = load().asq_quantize_act(
+                x.data_ptr(), _code(x.dtype), q.data_ptr(), _ptr(rs), M, K, act_mode, float(quant_scale),
+                _default_div_mode if div_mode is None else div_mode, 1 if fp8 else 0, _stream(dev),
+            )
+        _check(rc)
+        _launches += 1
+    if fp8:
+        q = q.view(torch.float8_e4m3fn)
+    return q, rs

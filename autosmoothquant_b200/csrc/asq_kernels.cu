@@ -1,0 +1,884 @@
+// asq_kernels.cu — B200 (sm_100a) SmoothQuant W8A8 / FP8 linear path: kernels + C ABI.
+//
+// One persistent, warp-specialised kernel per call (template: int8 | e4m3, N-tile width):
+//
+//   phase 1 (epilogue warps, all CTAs)   x[M,K] (fp32|fp16|bf16) -> 8-bit A panel in an L2-resident
+//       workspace.  One warp per token row: per-token absmax with warp shuffles, true IEEE division,
+//       rint, saturate.  Each finished row bumps a per-128-row-panel counter (release, gpu scope).
+//   phase 2 (same launch)                TMA producer warp waits (acquire) for the panel it is about
+//       to load, then streams 128x128-byte A and BNx128-byte W tiles (128B swizzle) through a
+//       multi-stage mbarrier ring; one elected thread issues tcgen05.mma (kind::i8 -> int32,
+//       kind::f8f6f4 -> fp32) into a double-buffered TMEM accumulator; 8 epilogue warps drain TMEM
+//       with tcgen05.ld, apply the reference's fp32 dequant (+bias) arithmetic op for op, convert and
+//       store, overlapping the next tile's main loop.
+//
+// Why the A operand takes one trip through L2 instead of being converted per CTA: every N-tile CTA
+// of an M panel would otherwise re-read the 16/32-bit activations and redo the division (N/BN times
+// the ALU work and 2-4x the shared-memory bytes per MMA step, which is already the limiter for 8-bit
+// operands).  Quantising once and letting TMA feed 8-bit tiles keeps the tensor pipe's operand
+// traffic at the minimum, and the panel counters let the GEMM start as soon as its first panel
+// exists, so no separate quantise / dequantise launch and no grid-wide barrier runs.
+//
+// Reference semantics (AniZpZ/AutoSmoothQuant): autosmoothquant/layers/nn/linear.py:83-106,
+// 172-208, 278-302 (INT8), :336-369, 413-427, 551-566 (FP8), functional/quantization.py:144-211,
+// csrc/int8gemm/cublasINT8MMWrapper.cc:224-354 (C = A . W^T, int32).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/asq.h"
+#include "asq_ptx.cuh"
+
+namespace asq {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 128;  // bytes == elements for 8-bit operands; one 128B swizzle row
+constexpr int UMMA_K = 32;    // K per tcgen05.mma for 8-bit operands
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int SYNC_EXIT = 0;                          // sync[0]: CTAs that finished; sync[1+p]: rows ready in panel p
+
+enum EpiKind : int { EPI_DEQUANT = 0, EPI_RAW_I32 = 1, EPI_ALPHA_BETA = 2 };
+
+struct LinearParams {
+  // phase 1
+  const void* x;         // nullptr: A is already 8-bit (tmA points at the caller's matrix)
+  uint8_t* a_q;          // [M,K] 8-bit workspace written by phase 1
+  float* row_scale;      // [M] workspace (per-token scales)
+  float* row_scale_out;  // optional copy for the caller
+  uint32_t* sync;        // phase counters, zero on entry, restored to zero on exit
+  float quant_scale, inv_quant_scale, inv_qmax, qmax;
+  // phase 2
+  void* y;
+  const float* bias;
+  const float* col_scale;
+  const void* bias_any;  // EPI_ALPHA_BETA bias (int8 / int32 / fp32)
+  float dequant_scale, alpha, beta;
+  int M, N, K;
+  int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
+  int num_m_blocks, num_n_blocks, num_k_blocks, group_n;
+};
+
+// ------------------------------------------------------------------ element helpers
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static constexpr int VEC = 4;  // elements per 16-byte load
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  __device__ static __forceinline__ float round_to(float v) { return v; }
+};
+template <>
+struct Elem<__half> {
+  static constexpr int VEC = 8;
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 t = __half22float2(h);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static __forceinline__ float round_to(float v) { return __half2float(__float2half_rn(v)); }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static __forceinline__ float round_to(float v) {
+    return __bfloat162float(__float2bfloat16_rn(v));
+  }
+};
+
+// sat_i8(rint(v)); NaN -> 0 (what torch's clamp + .to(int8) yields for the reference)
+__device__ __forceinline__ uint32_t cvt_s8(float v) {
+  int r;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return static_cast<uint32_t>(r) & 0xFFu;
+}
+// two floats -> two e4m3 bytes (round-to-nearest-even, saturate to +-448, NaN stays NaN):
+// identical to clamp(+-448) followed by torch's .to(float8_e4m3fn) (quantization.py:187-190)
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <bool FP8, int VEC>
+__device__ __forceinline__ void pack_store(uint8_t* dst, const float (&q)[VEC]) {
+  uint32_t w[VEC / 4];
+#pragma unroll
+  for (int i = 0; i < VEC / 4; ++i) {
+    if (FP8) {
+      w[i] = cvt_e4m3x2(q[4 * i], q[4 * i + 1]) | (cvt_e4m3x2(q[4 * i + 2], q[4 * i + 3]) << 16);
+    } else {
+      w[i] = cvt_s8(q[4 * i]) | (cvt_s8(q[4 * i + 1]) << 8) | (cvt_s8(q[4 * i + 2]) << 16) |
+             (cvt_s8(q[4 * i + 3]) << 24);
+    }
+  }
+  if (VEC == 8) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[VEC / 4 - 1]);
+  } else {
+    *reinterpret_cast<uint32_t*>(dst) = w[0];
+  }
+}
+
+// Quantise one token row with one warp.  Returns the row scale (per-token) or 0.
+//   ROUND       q = sat(rint(x))                                    linear.py:95
+//   SCALE       q = sat(rint(T(x / qs)))   division rounded to T    linear.py:290-292 / quantization.py:208-211
+//   PER_TOKEN   s = f32(T(absmax) / T(qmax)); q = sat(rint(f32(x)/s))   linear.py:88-92 / quantization.py:183-189
+// fp8: no rint, q = e4m3(clamp(v)).
+// Loads are issued in batches of QBATCH 16-byte vectors per lane (QBATCH*512 bytes per warp in
+// flight) so the phase is bandwidth- rather than latency-bound; a row that fits one batch
+// (K <= 4096 for 16-bit, 2048 for fp32 inputs) is read from HBM exactly once even per-token.
+constexpr int QBATCH = 16;
+
+template <typename T, bool FP8>
+__device__ __forceinline__ void quantize_vec(const uint4& v, uint8_t* dst, int mode, bool recip, float scale,
+                                             const LinearParams& p) {
+  constexpr int VEC = Elem<T>::VEC;
+  float f[VEC];
+  Elem<T>::unpack(v, f);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (mode == ASQ_ACT_PER_TOKEN) {
+      f[i] = __fdiv_rn(f[i], scale);  // fp32 tensor / fp32 tensor: true division on every device
+    } else if (mode == ASQ_ACT_SCALE) {
+      f[i] = Elem<T>::round_to(recip ? __fmul_rn(f[i], p.inv_quant_scale) : __fdiv_rn(f[i], p.quant_scale));
+    }
+  }
+  pack_store<FP8, VEC>(dst, f);
+}
+
+template <typename T>
+__device__ __forceinline__ float vec_absmax(const uint4& v, float amax) {
+  constexpr int VEC = Elem<T>::VEC;
+  float f[VEC];
+  Elem<T>::unpack(v, f);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) amax = fmaxf(amax, fabsf(f[i]));
+  return amax;
+}
+
+template <typename T>
+__device__ __forceinline__ float token_scale(float amax, const LinearParams& p) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  // absmax is exactly representable in T; the division by qmax happens in T (torch: fp32 math, one
+  // rounding to T).  CUDA torch multiplies by the fp32 reciprocal of a scalar divisor.
+  return (p.div_mode == ASQ_DIV_RECIPROCAL) ? Elem<T>::round_to(__fmul_rn(amax, p.inv_qmax))
+                                            : Elem<T>::round_to(__fdiv_rn(amax, p.qmax));
+}
+
+template <typename T, bool FP8>
+__device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_t* __restrict__ qrow,
+                                              int K, int lane, const LinearParams& p) {
+  constexpr int VEC = Elem<T>::VEC;
+  constexpr int STEP = 32 * VEC;          // elements one warp-wide vector load covers
+  constexpr int CHUNK = STEP * QBATCH;    // elements per batch
+  const int mode = p.act_mode;
+  const bool recip = (p.div_mode == ASQ_DIV_RECIPROCAL);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  float scale = 0.f;
+  uint4 buf[QBATCH];
+
+  if (mode == ASQ_ACT_PER_TOKEN) {
+    float amax = 0.f;
+    if (K <= CHUNK) {  // whole row lives in registers: one HBM read
+#pragma unroll
+      for (int j = 0; j < QBATCH; ++j) {
+        const int c = lane * VEC + j * STEP;
+        buf[j] = (c < K) ? __ldg(reinterpret_cast<const uint4*>(xrow + c)) : zero;
+      }
+#pragma unroll
+      for (int j = 0; j < QBATCH; ++j) amax = vec_absmax<T>(buf[j], amax);
+      scale = token_scale<T>(amax, p);
+#pragma unroll
+      for (int j = 0; j < QBATCH; ++j) {
+        const int c = lane * VEC + j * STEP;
+        if (c < K) quantize_vec<T, FP8>(buf[j], qrow + c, mode, recip, scale, p);
+      }
+      return scale;
+    }
+    for (int c0 = 0; c0 < K; c0 += CHUNK) {
+#pragma unroll
+      for (int j = 0; j < QBATCH; ++j) {
+        const int c = c0 + lane * VEC + j * STEP;
+        buf[j] = (c < K) ? __ldg(reinterpret_cast<const uint4*>(xrow + c)) : zero;
+      }
+#pragma unroll
+      for (int j = 0; j < QBATCH; ++j) amax = vec_absmax<T>(buf[j], amax);
+    }
+    scale = token_scale<T>(amax, p);
+  }
+  for (int c0 = 0; c0 < K; c0 += CHUNK) {  // second pass of a long per-token row re-reads it from L2
+#pragma unroll
+    for (int j = 0; j < QBATCH; ++j) {
+      const int c = c0 + lane * VEC + j * STEP;
+      buf[j] = (c < K) ? __ldg(reinterpret_cast<const uint4*>(xrow + c)) : zero;
+    }
+#pragma unroll
+    for (int j = 0; j < QBATCH; ++j) {
+      const int c = c0 + lane * VEC + j * STEP;
+      if (c < K) quantize_vec<T, FP8>(buf[j], qrow + c, mode, recip, scale, p);
+    }
+  }
+  return scale;
+}
+
+template <bool FP8>
+__device__ __forceinline__ float quantize_row_any(const LinearParams& p, int row, int lane) {
+  uint8_t* qrow = p.a_q + static_cast<size_t>(row) * p.K;
+  if (p.x_dtype == ASQ_BF16)
+    return quantize_row<__nv_bfloat16, FP8>(
+        reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<size_t>(row) * p.K, qrow, p.K, lane, p);
+  if (p.x_dtype == ASQ_F16)
+    return quantize_row<__half, FP8>(reinterpret_cast<const __half*>(p.x) + static_cast<size_t>(row) * p.K,
+                                     qrow, p.K, lane, p);
+  return quantize_row<float, FP8>(reinterpret_cast<const float*>(p.x) + static_cast<size_t>(row) * p.K, qrow,
+                                  p.K, lane, p);
+}
+
+// ------------------------------------------------------------------ epilogue
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ float load_bias_any(const void* b, int dtype, int col) {
+  if (dtype == ASQ_I8) return static_cast<float>(reinterpret_cast<const int8_t*>(b)[col]);
+  if (dtype == ASQ_I32) return static_cast<float>(reinterpret_cast<const int32_t*>(b)[col]);
+  return reinterpret_cast<const float*>(b)[col];
+}
+
+// One warp lane owns row `row`, 32 consecutive columns starting at col0; r[] = raw accumulators.
+template <bool FP8>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row, int col0, float rs,
+                                               const LinearParams& p) {
+  if (row >= p.M || col0 >= p.N) return;
+  const int N = p.N;
+  const int ncols = min(32, N - col0);
+  const size_t off = static_cast<size_t>(row) * N + col0;
+
+  if (p.epi_kind == EPI_RAW_I32) {
+    int32_t* dst = reinterpret_cast<int32_t*>(p.y) + off;
+    if (ncols == 32 && (N & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    } else {
+      for (int j = 0; j < ncols; ++j) dst[j] = static_cast<int32_t>(r[j]);
+    }
+    return;
+  }
+
+  float v[32];
+  if (p.epi_kind == EPI_DEQUANT) {
+    // reference order of operations (linear.py:93,104 / :197-207): factor first, then * acc, then + bias,
+    // each a separate fp32 rounding (no FMA contraction) so the result is bit-identical to torch.
+    const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN);
+    const float f_scalar = per_token ? __fmul_rn(p.dequant_scale, rs) : p.dequant_scale;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = col0 + j;
+      const float a = FP8 ? __uint_as_float(r[j]) : __int2float_rn(static_cast<int32_t>(r[j]));
+      float f = f_scalar;
+      if (p.col_scale != nullptr && j < ncols) {
+        f = __ldg(p.col_scale + c);
+        if (per_token) f = __fmul_rn(f, rs);
+      }
+      float t = __fmul_rn(f, a);
+      if (p.bias != nullptr && j < ncols) t = __fadd_rn(t, __ldg(p.bias + c));
+      v[j] = t;
+    }
+  } else {  // EPI_ALPHA_BETA: v = alpha*acc + beta*bias  (cublasLt o8 / csrc/kernels/linear.cu epilogues)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = __int2float_rn(static_cast<int32_t>(r[j]));
+      float t = __fmul_rn(p.alpha, a);
+      if (p.bias_any != nullptr && j < ncols)
+        t = __fadd_rn(t, __fmul_rn(p.beta, load_bias_any(p.bias_any, p.bias_dtype, col0 + j)));
+      if (p.flags & ASQ_EPI_RELU) t = fmaxf(t, 0.f);
+      v[j] = t;
+    }
+  }
+
+  switch (p.y_dtype) {
+    case ASQ_BF16:
+    case ASQ_F16: {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + off;
+      const bool bf = (p.y_dtype == ASQ_BF16);
+      if (ncols == 32 && (N & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          o.x = bf ? pack_bf16x2(v[j], v[j + 1]) : pack_f16x2(v[j], v[j + 1]);
+          o.y = bf ? pack_bf16x2(v[j + 2], v[j + 3]) : pack_f16x2(v[j + 2], v[j + 3]);
+          o.z = bf ? pack_bf16x2(v[j + 4], v[j + 5]) : pack_f16x2(v[j + 4], v[j + 5]);
+          o.w = bf ? pack_bf16x2(v[j + 6], v[j + 7]) : pack_f16x2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(dst + j) = o;
+        }
+      } else {
+        for (int j = 0; j < ncols; ++j) {
+          uint32_t w = bf ? pack_bf16x2(v[j], 0.f) : pack_f16x2(v[j], 0.f);
+          dst[j] = static_cast<uint16_t>(w & 0xFFFFu);
+        }
+      }
+      break;
+    }
+    case ASQ_F32: {
+      float* dst = reinterpret_cast<float*>(p.y) + off;
+      if (ncols == 32 && (N & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        for (int j = 0; j < ncols; ++j) dst[j] = v[j];
+      }
+      break;
+    }
+    case ASQ_I32: {
+      int32_t* dst = reinterpret_cast<int32_t*>(p.y) + off;
+      for (int j = 0; j < ncols; ++j) dst[j] = __float2int_rn(v[j]);
+      break;
+    }
+    case ASQ_I8: {
+      int8_t* dst = reinterpret_cast<int8_t*>(p.y) + off;
+      if (ncols == 32 && (N & 15) == 0) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          w[j] = cvt_s8(v[4 * j]) | (cvt_s8(v[4 * j + 1]) << 8) | (cvt_s8(v[4 * j + 2]) << 16) |
+                 (cvt_s8(v[4 * j + 3]) << 24);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      } else {
+        for (int j = 0; j < ncols; ++j) dst[j] = static_cast<int8_t>(cvt_s8(v[j]));
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// ------------------------------------------------------------------ tile schedule
+// Tiles are walked M-panel by M-panel with N fastest, inside groups of `group_n` N-blocks sized so one
+// group's W tiles stay L2-resident.  Walking panels in order lets the first wave start as soon as the
+// first panels of phase 1 exist while later panels are still being quantised.
+__device__ __forceinline__ void tile_coords(int t, const LinearParams& p, int& m_blk, int& n_blk) {
+  const int group_size = p.group_n * p.num_m_blocks;
+  const int g = t / group_size;
+  const int first_n = g * p.group_n;
+  const int gn = min(p.num_n_blocks - first_n, p.group_n);
+  const int local = t - g * group_size;
+  m_blk = local / gn;
+  n_blk = first_n + local % gn;
+}
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K;
+  static constexpr uint32_t B_BYTES = BN * BLOCK_K;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr uint32_t BAR_OFFSET = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+// ------------------------------------------------------------------ the kernel
+template <bool FP8, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const LinearParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+
+  const uint32_t bar_base = base + Cfg::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::BAR_OFFSET + 8u * (2 * STAGES + 4));
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_blocks * p.num_n_blocks;
+  const bool fused = (p.x != nullptr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(t, p, m_blk, n_blk);
+        bool panel_ready = !fused;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+          // W does not depend on phase 1: issue it before (possibly) waiting for the A panel
+          tma_load_2d(base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES, &tmB, full_bar(stage),
+                      kb * BLOCK_K, n_blk * BN);
+          if (!panel_ready) {
+            const uint32_t need = static_cast<uint32_t>(min(BLOCK_M, p.M - m_blk * BLOCK_M));
+            const uint32_t* flag = p.sync + 1 + m_blk;
+            while (ld_acquire_gpu(flag) < need) __nanosleep(64);
+            fence_proxy_async_all();  // phase-1 generic-proxy stores -> TMA (async proxy) reads
+            panel_ready = true;
+          }
+          tma_load_2d(base + stage * Cfg::A_BYTES, &tmA, full_bar(stage), kb * BLOCK_K,
+                      m_blk * BLOCK_M);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(FP8, BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(base + stage * Cfg::A_BYTES);
+          const uint64_t bdesc = make_smem_desc_sw128(base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            const uint64_t koff = static_cast<uint64_t>(k * (UMMA_K >> 4));
+            if (FP8) mma_f8(d_tmem, adesc + koff, bdesc + koff, idesc, (kb | k) != 0);
+            else     mma_i8(d_tmem, adesc + koff, bdesc + koff, idesc, (kb | k) != 0);
+          }
+          mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== phase 1: activation quantisation =====================
+    const int ew = warp - 2;  // 0..7
+    if (fused) {
+      const int warps_total = NUM_EPI_WARPS * gridDim.x;
+      for (int row = ew * gridDim.x + blockIdx.x; row < p.M; row += warps_total) {
+        const float s = quantize_row_any<FP8>(p, row, lane);
+        if (lane == 0 && p.act_mode == ASQ_ACT_PER_TOKEN) {
+          p.row_scale[row] = s;
+          if (p.row_scale_out != nullptr) p.row_scale_out[row] = s;
+        }
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          red_release_gpu_add(p.sync + 1 + row / BLOCK_M, 1u);
+        }
+      }
+    }
+    // ===================== phase 2: epilogue =====================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;           // which half of the BN columns
+    constexpr int CHUNKS = BN / 2 / 32; // 32-column chunks per warp
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(t, p, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      float rs = 0.f;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (p.act_mode == ASQ_ACT_PER_TOKEN && p.epi_kind == EPI_DEQUANT && row < p.M)
+        rs = __ldcg(p.row_scale + row);
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int col_in_tile = half * (BN / 2) + ch * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_in_tile, r);
+        tmem_ld_wait();
+        epilogue_chunk<FP8>(r, row, n_blk * BN + col_in_tile, rs, p);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (fused && threadIdx.x == 0) {
+    // last CTA out restores the phase counters so the workspace is reusable by the next launch
+    __threadfence();
+    const uint32_t done = atomicAdd(p.sync + SYNC_EXIT, 1u);
+    if (done == gridDim.x - 1) {
+      for (int i = 0; i < p.num_m_blocks; ++i) p.sync[1 + i] = 0u;
+      p.sync[SYNC_EXIT] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// Stand-alone prologue (debug / parity tap): same row routine, no GEMM.
+template <bool FP8>
+__global__ void __launch_bounds__(256) asq_quantize_kernel(const LinearParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < p.M; row += warps_total) {
+    const float s = quantize_row_any<FP8>(p, row, lane);
+    if (lane == 0 && p.act_mode == ASQ_ACT_PER_TOKEN && p.row_scale != nullptr) p.row_scale[row] = s;
+  }
+}
+
+}  // namespace asq
+
+// ====================================================================== host side
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+struct DeviceState {
+  bool probed = false;
+  bool supported = false;
+  int sm_count = 0;
+  bool attrs_set = false;
+};
+constexpr int kMaxDevices = 64;
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+EncodeTiledFn g_encode = nullptr;
+
+int get_device(int* dev_out, DeviceState** st_out) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ASQ_ERR_CUDA, "no CUDA device available: %s", cudaGetErrorString(e));
+  }
+  if (dev < 0 || dev >= kMaxDevices) return fail(ASQ_ERR_CUDA, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceState& st = g_dev[dev];
+  if (!st.probed) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    st.supported = (prop.major == 10 && prop.minor == 0);
+    st.sm_count = prop.multiProcessorCount;
+    st.probed = true;
+  }
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+      return fail(ASQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *dev_out = dev;
+  *st_out = &st;
+  return ASQ_OK;
+}
+
+// 2-D map over a row-major [rows, K] byte matrix, box = [box_rows, 128 bytes], 128B swizzle.
+int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(K)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(asq::BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                        estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ASQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return ASQ_OK;
+}
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  uint8_t* a_q;
+  float* row_scale;
+  uint32_t* sync;
+};
+// Layout: [phase counters: fixed kSyncBytes] [row scales: M fp32] [8-bit copy of x: M*K].  The counters
+// sit at a fixed offset so a cached, zero-initialised buffer stays valid when M and K change.
+constexpr size_t kSyncBytes = 32768;  // 8192 counters -> up to 8191 panels (about 1M rows)
+size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
+  const size_t rs = round_up(static_cast<size_t>(M) * 4, 1024);
+  const size_t aq = round_up(static_cast<size_t>(M) * K, 1024);
+  if (w != nullptr) {
+    uint8_t* b = static_cast<uint8_t*>(base);
+    w->sync = reinterpret_cast<uint32_t*>(b);
+    w->row_scale = reinterpret_cast<float*>(b + kSyncBytes);
+    w->a_q = b + kSyncBytes + rs;
+  }
+  return kSyncBytes + rs + aq;
+}
+
+template <bool FP8, int BN>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const asq::LinearParams& p, int grid,
+               cudaStream_t stream) {
+  using Cfg = asq::TileCfg<BN>;
+  auto kern = asq::asq_linear_kernel<FP8, BN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  kern<<<grid, asq::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return ASQ_OK;
+}
+
+// Shared launcher: `a8` is the 8-bit A matrix TMA reads (caller's matrix, or the workspace copy).
+int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p, cudaStream_t stream) {
+  int dev;
+  DeviceState* st;
+  int rc = get_device(&dev, &st);
+  if (rc != ASQ_OK) return rc;
+  if (!st->supported)
+    return fail(ASQ_ERR_CUDA, "device %d is not compute capability 10.0 (sm_100a kernels only)", dev);
+
+  const int bn = (p.N > 128) ? 256 : (p.N > 64 ? 128 : 64);
+  p.num_m_blocks = (p.M + asq::BLOCK_M - 1) / asq::BLOCK_M;
+  p.num_n_blocks = (p.N + bn - 1) / bn;
+  p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
+  {  // keep one group's W tiles (group_n * bn * K bytes) within ~48 MB of the 126 MB L2
+    const long long per_block = static_cast<long long>(bn) * p.K;
+    long long gn = (48ll << 20) / per_block;
+    p.group_n = static_cast<int>(gn < 1 ? 1 : (gn > p.num_n_blocks ? p.num_n_blocks : gn));
+  }
+  const long long tiles = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
+  const int grid = static_cast<int>(tiles < st->sm_count ? tiles : st->sm_count);
+
+  CUtensorMap tmA, tmB;
+  rc = make_tmap(&tmA, a8, p.M, p.K, asq::BLOCK_M);
+  if (rc != ASQ_OK) return rc;
+  rc = make_tmap(&tmB, w, p.N, p.K, bn);
+  if (rc != ASQ_OK) return rc;
+
+  if (fp8) {
+    if (bn == 256) return launch_cfg<true, 256>(tmA, tmB, p, grid, stream);
+    if (bn == 128) return launch_cfg<true, 128>(tmA, tmB, p, grid, stream);
+    return launch_cfg<true, 64>(tmA, tmB, p, grid, stream);
+  }
+  if (bn == 256) return launch_cfg<false, 256>(tmA, tmB, p, grid, stream);
+  if (bn == 128) return launch_cfg<false, 128>(tmA, tmB, p, grid, stream);
+  return launch_cfg<false, 64>(tmA, tmB, p, grid, stream);
+}
+
+int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {
+  if (M < 0 || N <= 0 || K <= 0) return fail(ASQ_ERR_INVALID, "bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  if (K % 16 != 0) return fail(ASQ_ERR_INVALID, "K=%lld must be a multiple of 16 (TMA row pitch)", (long long)K);
+  if (M > 0x7fffff00LL || N > 0x7fffff00LL || K > 0x7fffff00LL) return fail(ASQ_ERR_INVALID, "dimension too large");
+  if (M == 0) return ASQ_OK;
+  if (a == nullptr || w == nullptr || y == nullptr) return fail(ASQ_ERR_INVALID, "null pointer argument");
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+      (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(ASQ_ERR_INVALID, "x, w and y must be 16-byte aligned");
+  return ASQ_OK;
+}
+
+bool is_float_dtype(int d) { return d == ASQ_F32 || d == ASQ_F16 || d == ASQ_BF16; }
+
+int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype,
+                 int64_t M, int64_t N, int64_t K, int act_mode, float quant_scale, float dequant_scale,
+                 const float* col_scale, float* row_scale_out, int div_mode, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, w, y, M, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (!is_float_dtype(x_dtype) || !is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "x/y dtype must be f32, f16 or bf16");
+  if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
+  if (act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC)
+    return fail(ASQ_ERR_UNSUPPORTED, "per-tensor dynamic activation scale is not implemented in the fused kernel");
+  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN)
+    return fail(ASQ_ERR_INVALID, "bad act_mode %d", act_mode);
+  if (fp8 && act_mode == ASQ_ACT_ROUND) return fail(ASQ_ERR_INVALID, "ASQ_ACT_ROUND is int8-only");
+  if (M == 0) return ASQ_OK;
+  if ((M + asq::BLOCK_M - 1) / asq::BLOCK_M + 1 > static_cast<int64_t>(kSyncBytes / 4))
+    return fail(ASQ_ERR_UNSUPPORTED, "M=%lld exceeds the %zu row panels one launch tracks; split the batch", (long long)M, kSyncBytes / 4 - 1);
+  if (workspace == nullptr || workspace_bytes < asq_workspace_bytes(M, K))
+    return fail(ASQ_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", asq_workspace_bytes(M, K), workspace_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(ASQ_ERR_INVALID, "workspace must be 1024-byte aligned");
+
+  Workspace ws;
+  ws_layout(M, K, workspace, &ws);
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.row_scale_out = row_scale_out; p.sync = ws.sync;
+  p.quant_scale = quant_scale; p.inv_quant_scale = 1.0f / quant_scale;
+  p.qmax = fp8 ? 448.0f : 127.0f; p.inv_qmax = 1.0f / p.qmax;
+  p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.x_dtype = x_dtype; p.y_dtype = y_dtype; p.act_mode = act_mode; p.div_mode = div_mode;
+  p.epi_kind = asq::EPI_DEQUANT;
+  return launch_linear(fp8, ws.a_q, w, p, static_cast<cudaStream_t>(stream));
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int asq_version(void) { return ASQ_VERSION; }
+const char* asq_last_error(void) { return g_err; }
+
+int asq_device_supported(void) {
+  int dev;
+  DeviceState* st;
+  if (get_device(&dev, &st) != ASQ_OK) return 0;
+  return st->supported ? 1 : 0;
+}
+
+size_t asq_workspace_bytes(int64_t M, int64_t K) {
+  if (M <= 0 || K <= 0) return 1024;
+  return ws_layout(M, K, nullptr, nullptr);
+}
+
+int asq_w8a8_linear(const void* x, int x_dtype, const int8_t* w, const float* bias, void* y, int y_dtype,
+                    int64_t M, int64_t N, int64_t K, int act_mode, float quant_scale, float dequant_scale,
+                    const float* col_scale, float* row_scale_out, int div_mode, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return fused_linear(false, x, x_dtype, w, bias, y, y_dtype, M, N, K, act_mode, quant_scale, dequant_scale,
+                      col_scale, row_scale_out, div_mode, workspace, workspace_bytes, stream);
+}
+
+int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const float* bias, void* y, int y_dtype,
+                   int64_t M, int64_t N, int64_t K, int act_mode, float in_scale, float w_scale,
+                   float* row_scale_out, int div_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  // per-token: y = acc * (w_scale * s[m]); static: y = acc * (w_scale * in_scale)
+  const float ds = (act_mode == ASQ_ACT_PER_TOKEN) ? w_scale : w_scale * in_scale;
+  return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, in_scale, ds, nullptr,
+                      row_scale_out, div_mode, workspace, workspace_bytes, stream);
+}
+
+int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c, int64_t M, int64_t N, int64_t K, void* stream) {
+  int rc = check_common(a, w, c, M, N, K);
+  if (rc != ASQ_OK || M == 0) return rc;
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = c; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = ASQ_I32; p.epi_kind = asq::EPI_RAW_I32; p.act_mode = ASQ_ACT_ROUND;
+  return launch_linear(false, a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_dtype, void* y, int y_dtype,
+                   int64_t M, int64_t N, int64_t K, float alpha, float beta, int flags, void* stream) {
+  int rc = check_common(a, w, y, M, N, K);
+  if (rc != ASQ_OK || M == 0) return rc;
+  if (y_dtype != ASQ_I8 && y_dtype != ASQ_I32 && !is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "bad y_dtype %d", y_dtype);
+  if (bias != nullptr && bias_dtype != ASQ_I8 && bias_dtype != ASQ_I32 && bias_dtype != ASQ_F32)
+    return fail(ASQ_ERR_INVALID, "bias dtype must be i8, i32 or f32");
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = y; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_ALPHA_BETA; p.act_mode = ASQ_ACT_ROUND;
+  p.alpha = alpha; p.beta = beta; p.bias_any = bias; p.bias_dtype = bias_dtype; p.flags = flags;
+  return launch_linear(false, a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale, int64_t M, int64_t K, int act_mode,
+                     float quant_scale, int div_mode, int fp8, void* stream) {
+  if (M < 0 || K <= 0 || K % 16 != 0) return fail(ASQ_ERR_INVALID, "bad shape M=%lld K=%lld (K %% 16 == 0 required)", (long long)M, (long long)K);
+  if (!is_float_dtype(x_dtype)) return fail(ASQ_ERR_INVALID, "x dtype must be f32, f16 or bf16");
+  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN)
+    return fail(act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC ? ASQ_ERR_UNSUPPORTED : ASQ_ERR_INVALID, "unsupported act_mode %d", act_mode);
+  if (M == 0) return ASQ_OK;
+  if (x == nullptr || q == nullptr) return fail(ASQ_ERR_INVALID, "null pointer argument");
+  if (act_mode == ASQ_ACT_PER_TOKEN && row_scale == nullptr) return fail(ASQ_ERR_INVALID, "row_scale required for per-token");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(q) & 15))
+    return fail(ASQ_ERR_INVALID, "x and q must be 16-byte aligned");
+  int dev;
+  DeviceState* st;
+  int rc = get_device(&dev, &st);
+  if (rc != ASQ_OK) return rc;
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.a_q = static_cast<uint8_t*>(q); p.row_scale = row_scale;
+  p.quant_scale = quant_scale; p.inv_quant_scale = 1.0f / quant_scale;
+  p.qmax = fp8 ? 448.0f : 127.0f; p.inv_qmax = 1.0f / p.qmax;
+  p.M = static_cast<int>(M); p.K = static_cast<int>(K);
+  p.x_dtype = x_dtype; p.act_mode = act_mode; p.div_mode = div_mode;
+  const int rows_per_block = 8;
+  long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  const long long cap = static_cast<long long>(st->sm_count) * 8;
+  if (blocks > cap) blocks = cap;
+  if (fp8) asq::asq_quantize_kernel<true><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else     asq::asq_quantize_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return ASQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+/*
+ * asq.h — C ABI of the B200-native (sm_100a) SmoothQuant W8A8 / FP8 linear path.
+ *
+ * This shared library (libasq_b200.so) is the drop-in boundary for the native
+ * extension of AniZpZ/AutoSmoothQuant (`autosmoothquant._CUDA`) plus the eager
+ * quantize / dequantize launches the reference's Python modules run around it.
+ * Plain pointers and sizes only: no torch types cross this boundary.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   - csrc/int8gemm/bindings.cpp:69-84   I8CUGEMM::linear_a8_w8_o32_   -> asq_i8gemm_o32
+ *   - csrc/int8gemm/bindings.cpp:52-67   I8CUGEMM::linear_a8_w8_o32    -> asq_i8gemm_o32
+ *   - csrc/int8gemm/bindings.cpp:86-142  linear_a8_w8_o8[_], _b8_o8_   -> asq_i8gemm_o8
+ *   - autosmoothquant/layers/nn/linear.py:83-106   W8A8BFP32OFP32Linear.forward
+ *   - autosmoothquant/layers/nn/linear.py:172-208  W8A8BFP32OFP32QKVLinear.forward
+ *   - autosmoothquant/layers/nn/linear.py:278-302  ...LinearWithQuantScale.forward
+ *                                                                      -> asq_w8a8_linear
+ *   - autosmoothquant/layers/nn/linear.py:336-369, 413-427, 551-566
+ *       easy_fp8_gemm / FP8LinearDynamic.forward / FP8LinearStatic.forward
+ *                                                                      -> asq_fp8_linear
+ *   - autosmoothquant/layers/functional/quantization.py:173-191, 208-211 and the
+ *     inline quantisation in linear.py:88-95,283-292                   -> asq_quantize_act
+ *
+ * Conventions
+ *   - Every entry point returns ASQ_OK (0) or a negative asq_status and never
+ *     throws; asq_last_error() returns a thread-local description of the last
+ *     failure on the calling thread.
+ *   - All device pointers must belong to the CUDA device that is current on the
+ *     calling thread; `stream` is a cudaStream_t passed as void*. Calls are
+ *     asynchronous with respect to the host, stateless and re-entrant.
+ *   - Matrices are dense row-major: x [M,K], w [N,K] (K contiguous, i.e. the
+ *     "TN" GEMM of cublasINT8MMWrapper.cc:246-253), y [M,N].
+ *   - K must be a multiple of 16 (TMA row pitch); M, N arbitrary (M may be 0).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point
+ *     returns ASQ_ERR_CUDA.
+ */
+#ifndef ASQ_H_
+#define ASQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASQ_VERSION 100 /* major*100 + minor */
+
+typedef enum asq_status {
+  ASQ_OK = 0,
+  ASQ_ERR_INVALID = -1,     /* bad argument (null pointer, misaligned, bad enum, K%16!=0) */
+  ASQ_ERR_UNSUPPORTED = -2, /* valid request this build does not implement */
+  ASQ_ERR_CUDA = -3,        /* CUDA runtime / driver error, or no sm_100 device */
+  ASQ_ERR_WORKSPACE = -4    /* workspace too small or not provided */
+} asq_status;
+
+/* Element types of x / y buffers. */
+typedef enum asq_dtype {
+  ASQ_F32 = 0,
+  ASQ_F16 = 1,
+  ASQ_BF16 = 2,
+  ASQ_I32 = 3, /* y only: raw accumulator (int8 path) */
+  ASQ_I8 = 4   /* y only: requantised output (asq_i8gemm_o8) */
+} asq_dtype;
+
+/* Activation quantisation applied by the fused prologue.
+ *   ASQ_ACT_ROUND      q = sat(rint(x))                      linear.py:95   (scale folded into the norm)
+ *   ASQ_ACT_SCALE      q = sat(rint(T(x / quant_scale)))     linear.py:290-292 (division rounded to x's dtype T)
+ *   ASQ_ACT_PER_TOKEN  s[m] = f32(T(max_k|x[m,k]|) / T(qmax)); q = sat(rint(f32(x)/s[m]))   linear.py:88-92
+ *   ASQ_ACT_PER_TENSOR_DYNAMIC (fp8 only) s = T(max|x|)/T(448) over the whole tensor, q = T(x/s)
+ *                                                            quantization.py:144-170
+ * qmax is 127 for int8 and 448 for e4m3.                                                   */
+typedef enum asq_act_mode {
+  ASQ_ACT_ROUND = 0,
+  ASQ_ACT_SCALE = 1,
+  ASQ_ACT_PER_TOKEN = 2,
+  ASQ_ACT_PER_TENSOR_DYNAMIC = 3
+} asq_act_mode;
+
+/* How `tensor / python_scalar` is evaluated.  torch on CUDA multiplies by the
+ * fp32 reciprocal of a scalar divisor, torch on CPU performs a true division;
+ * the two differ in the last bit.  ASQ_DIV_RECIPROCAL reproduces the reference
+ * running on its only supported device (CUDA); ASQ_DIV_EXACT reproduces the
+ * reference's Python executed on CPU (what the oracle is pinned against). */
+typedef enum asq_div_mode { ASQ_DIV_RECIPROCAL = 0, ASQ_DIV_EXACT = 1 } asq_div_mode;
+
+/* Epilogue flags for asq_i8gemm_epi (csrc/kernels/linear.cu variants). */
+typedef enum asq_epi_flags {
+  ASQ_EPI_RELU = 1 /* clamp negative results to zero before the output conversion */
+} asq_epi_flags;
+
+int asq_version(void);
+const char* asq_last_error(void);
+
+/* 1 if the current CUDA device can run the kernels (compute capability 10.0), else 0. */
+int asq_device_supported(void);
+
+/* Bytes of scratch the fused entry points need for an [M,K] activation:
+ * the int8/e4m3 copy of x, M fp32 row scales and the phase counters.  The
+ * buffer must be 1024-byte aligned device memory, zero-filled once when
+ * allocated (the kernels restore the counters to zero before they exit), and
+ * must not be shared by calls that may run concurrently. */
+size_t asq_workspace_bytes(int64_t M, int64_t K);
+
+/* y = dequant( quant(x) . w^T ) [+ bias], one launch.
+ *   x         [M,K] x_dtype in {F32,F16,BF16}
+ *   w         [N,K] int8
+ *   bias      [N] fp32 or NULL
+ *   y         [M,N] y_dtype in {F32,F16,BF16}
+ *   dequant_scale   scalar applied to every column, used when col_scale == NULL
+ *   col_scale [N] fp32 or NULL: per-output-column dequant scale (the QKV variant's
+ *             piecewise-constant q/k/v scales, linear.py:197-200)
+ *   row_scale_out [M] fp32 or NULL: receives the per-token scales (ASQ_ACT_PER_TOKEN)
+ * Arithmetic (bit-exact with the reference's fp32 epilogue):
+ *   f = col_scale ? col_scale[n] : dequant_scale;  per-token: f = f * s[m]
+ *   y[m,n] = T( f * f32(acc[m,n]) (+ bias[n]) )     acc = exact int32 dot product       */
+int asq_w8a8_linear(const void* x, int x_dtype, const int8_t* w, const float* bias,
+                    void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                    int act_mode, float quant_scale, float dequant_scale,
+                    const float* col_scale, float* row_scale_out, int div_mode,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* FP8-e4m3 twin: y = T( (sum_k q[m,k]*w[n,k]) * (s_x * w_scale) (+ bias) ), fp32 accumulate
+ * on the tensor cores (the reference dequantises both operands and calls F.linear,
+ * linear.py:363-368).
+ *   w  [N,K] e4m3 bytes;  act_mode in {SCALE (static, in_scale), PER_TOKEN, PER_TENSOR_DYNAMIC} */
+int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const float* bias,
+                   void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                   int act_mode, float in_scale, float w_scale,
+                   float* row_scale_out, int div_mode,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* c[M,N] (int32) = a[M,K] (int8) . w[N,K]^T (int8), exact.  Drop-in for
+ * I8CUGEMM::linear_a8_w8_o32_ and the exactness tap of the fused kernels. */
+int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c,
+                   int64_t M, int64_t N, int64_t K, void* stream);
+
+/* INT8-in GEMM with a scaling epilogue (the o8 methods of I8CUGEMM and the
+ * csrc/kernels/linear.cu variants):
+ *   v = alpha * f32(acc) + beta * bias            (bias [N]: int8, int32 or fp32 per bias_dtype, or NULL)
+ *   y = y_dtype == I8 ? sat_i8(rint(v)) : y_dtype == I32 ? rint(v) : v     (ReLU first if flagged) */
+int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_dtype,
+                   void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                   float alpha, float beta, int flags, void* stream);
+
+/* Debug / parity tap of the fused prologue: writes the quantised activations
+ * (int8, or e4m3 bytes when fp8 != 0) and, for per-token, the row scales. */
+int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale,
+                     int64_t M, int64_t K, int act_mode, float quant_scale,
+                     int div_mode, int fp8, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASQ_H_ */
