@@ -20,7 +20,7 @@ LIB_PATH = _PKG_DIR / "libasq_b200.so"
 
 # enums of include/asq.h
 ASQ_F32, ASQ_F16, ASQ_BF16, ASQ_I32, ASQ_I8 = 0, 1, 2, 3, 4
-ACT_ROUND, ACT_SCALE, ACT_PER_TOKEN, ACT_PER_TENSOR_DYNAMIC = 0, 1, 2, 3
+ACT_ROUND, ACT_SCALE, ACT_PER_TOKEN, ACT_PER_TENSOR_DYNAMIC, ACT_ROW_SCALE_GIVEN = 0, 1, 2, 3, 4
 DIV_RECIPROCAL, DIV_EXACT = 0, 1
 EPI_RELU = 1
 
@@ -326,6 +326,7 @@ def quantize_act(
     quant_scale: float = 1.0,
     fp8: bool = False,
     div_mode: Optional[int] = None,
+    row_scale: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Parity tap of the fused prologue: returns (q [M,K] int8 | float8_e4m3fn, row_scale [M] or None)."""
     global _launches
@@ -336,7 +337,12 @@ def quantize_act(
         x = x.contiguous()
     M, K = x.shape
     q = torch.empty((M, K), dtype=torch.uint8 if fp8 else torch.int8, device=dev)
-    rs = torch.empty((M,), dtype=torch.float32, device=dev) if act_mode == ACT_PER_TOKEN else None
+    if act_mode == ACT_ROW_SCALE_GIVEN:
+        if row_scale is None or row_scale.dtype != torch.float32 or row_scale.numel() != M:
+            raise ValueError("ACT_ROW_SCALE_GIVEN needs row_scale: float32 [M]")
+        rs = row_scale.contiguous()
+    else:
+        rs = torch.empty((M,), dtype=torch.float32, device=dev) if act_mode == ACT_PER_TOKEN else None
     if M > 0:
         with torch.cuda.device(dev):
             rc = load().asq_quantize_act(

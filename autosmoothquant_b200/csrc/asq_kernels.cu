@@ -28,6 +28,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -51,6 +52,7 @@ struct LinearParams {
   uint8_t* a_q;          // [M,K] 8-bit workspace written by phase 1
   float* row_scale;      // [M] workspace (per-token scales)
   float* row_scale_out;  // optional copy for the caller
+  const float* row_scale_in;  // ASQ_ACT_ROW_SCALE_GIVEN: per-token scales supplied by the caller
   uint32_t* sync;        // phase counters, zero on entry, restored to zero on exit
   float quant_scale, inv_quant_scale, inv_qmax, qmax;
   // phase 2
@@ -157,7 +159,7 @@ __device__ __forceinline__ void quantize_vec(const uint4& v, uint8_t* dst, int m
   Elem<T>::unpack(v, f);
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    if (mode == ASQ_ACT_PER_TOKEN) {
+    if (mode == ASQ_ACT_PER_TOKEN || mode == ASQ_ACT_ROW_SCALE_GIVEN) {
       f[i] = __fdiv_rn(f[i], scale);  // fp32 tensor / fp32 tensor: true division on every device
     } else if (mode == ASQ_ACT_SCALE) {
       f[i] = Elem<T>::round_to(recip ? __fmul_rn(f[i], p.inv_quant_scale) : __fdiv_rn(f[i], p.quant_scale));
@@ -188,7 +190,7 @@ __device__ __forceinline__ float token_scale(float amax, const LinearParams& p) 
 
 template <typename T, bool FP8>
 __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_t* __restrict__ qrow,
-                                              int K, int lane, const LinearParams& p) {
+                                              int K, int lane, const LinearParams& p, float given_scale) {
   constexpr int VEC = Elem<T>::VEC;
   constexpr int STEP = 32 * VEC;          // elements one warp-wide vector load covers
   constexpr int CHUNK = STEP * QBATCH;    // elements per batch
@@ -198,6 +200,7 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
   float scale = 0.f;
   uint4 buf[QBATCH];
 
+  if (mode == ASQ_ACT_ROW_SCALE_GIVEN) scale = given_scale;
   if (mode == ASQ_ACT_PER_TOKEN) {
     float amax = 0.f;
     if (K <= CHUNK) {  // whole row lives in registers: one HBM read
@@ -245,14 +248,13 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
 template <bool FP8>
 __device__ __forceinline__ float quantize_row_any(const LinearParams& p, int row, int lane) {
   uint8_t* qrow = p.a_q + static_cast<size_t>(row) * p.K;
+  const size_t off = static_cast<size_t>(row) * p.K;
+  const float given = (p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? __ldg(p.row_scale_in + row) : 0.f;
   if (p.x_dtype == ASQ_BF16)
-    return quantize_row<__nv_bfloat16, FP8>(
-        reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<size_t>(row) * p.K, qrow, p.K, lane, p);
+    return quantize_row<__nv_bfloat16, FP8>(reinterpret_cast<const __nv_bfloat16*>(p.x) + off, qrow, p.K, lane, p, given);
   if (p.x_dtype == ASQ_F16)
-    return quantize_row<__half, FP8>(reinterpret_cast<const __half*>(p.x) + static_cast<size_t>(row) * p.K,
-                                     qrow, p.K, lane, p);
-  return quantize_row<float, FP8>(reinterpret_cast<const float*>(p.x) + static_cast<size_t>(row) * p.K, qrow,
-                                  p.K, lane, p);
+    return quantize_row<__half, FP8>(reinterpret_cast<const __half*>(p.x) + off, qrow, p.K, lane, p, given);
+  return quantize_row<float, FP8>(reinterpret_cast<const float*>(p.x) + off, qrow, p.K, lane, p, given);
 }
 
 // ------------------------------------------------------------------ epilogue
@@ -296,7 +298,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
   if (p.epi_kind == EPI_DEQUANT) {
     // reference order of operations (linear.py:93,104 / :197-207): factor first, then * acc, then + bias,
     // each a separate fp32 rounding (no FMA contraction) so the result is bit-identical to torch.
-    const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN);
+    const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN);
     const float f_scalar = per_token ? __fmul_rn(p.dequant_scale, rs) : p.dequant_scale;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -396,22 +398,28 @@ __device__ __forceinline__ void tile_coords(int t, const LinearParams& p, int& m
   n_blk = first_n + local % gn;
 }
 
-template <int BN>
+// BN = accumulator width (UMMA N).  CG = CTAs per tile: 1 -> a 128 x BN tile per CTA; 2 -> a CTA pair
+// (cta_group::2) owns a 256 x BN tile: each CTA stages its own 128 A rows and HALF of the W tile, the
+// leader issues 256 x BN MMAs that read both CTAs' shared memory, each CTA drains its own 128 TMEM lanes.
+// Pairing halves the W bytes every SM pulls from L2 per MMA, which is what bounds 8-bit GEMMs here.
+template <int BN, int CG>
 struct TileCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K;
-  static constexpr uint32_t B_BYTES = BN * BLOCK_K;
+  static constexpr uint32_t B_ROWS = BN / CG;  // W rows staged per CTA
+  static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K;
+  static constexpr int STAGES = (192 * 1024) / (A_BYTES + B_BYTES) > 8 ? 8 : (192 * 1024) / (A_BYTES + B_BYTES);
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator
   static constexpr uint32_t BAR_OFFSET = STAGES * (A_BYTES + B_BYTES);
   static constexpr uint32_t SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int TILE_M = BLOCK_M * CG;
 };
 
 // ------------------------------------------------------------------ the kernel
-template <bool FP8, int BN>
+template <bool FP8, int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const LinearParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -429,70 +437,77 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_blocks * p.num_n_blocks;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int num_workers = gridDim.x / CG;                        // CTAs (CG=1) or CTA pairs (CG=2)
+  const int worker = blockIdx.x / CG;
+  const int total_tiles = p.num_m_blocks * p.num_n_blocks;       // num_m_blocks counts TILE_M-row tiles
   const bool fused = (p.x != nullptr);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx; TMA bytes of both CTAs land here
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS * CG);  // epilogue warps of every CTA of the pair
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else         { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // peer barriers must exist before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = worker; t < total_tiles; t += num_workers) {
         int m_blk, n_blk;
         tile_coords(t, p, m_blk, n_blk);
-        bool panel_ready = !fused;
+        const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's A rows
+        bool panel_ready = !fused || row0 >= p.M;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+          if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+          const uint32_t sA = base + stage * Cfg::A_BYTES;
+          const uint32_t sB = base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES;
+          const int w_row = n_blk * BN + static_cast<int>(cta_rank) * static_cast<int>(Cfg::B_ROWS);
           // W does not depend on phase 1: issue it before (possibly) waiting for the A panel
-          tma_load_2d(base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES, &tmB, full_bar(stage),
-                      kb * BLOCK_K, n_blk * BN);
+          if (CG == 2) tma_load_2d_pair(sB, &tmB, full_bar(stage), kb * BLOCK_K, w_row);
+          else         tma_load_2d(sB, &tmB, full_bar(stage), kb * BLOCK_K, w_row);
           if (!panel_ready) {
-            const uint32_t need = static_cast<uint32_t>(min(BLOCK_M, p.M - m_blk * BLOCK_M));
-            const uint32_t* flag = p.sync + 1 + m_blk;
+            const uint32_t need = static_cast<uint32_t>(min(BLOCK_M, p.M - row0));
+            const uint32_t* flag = p.sync + 1 + row0 / BLOCK_M;
             while (ld_acquire_gpu(flag) < need) __nanosleep(64);
             fence_proxy_async_all();  // phase-1 generic-proxy stores -> TMA (async proxy) reads
             panel_ready = true;
           }
-          tma_load_2d(base + stage * Cfg::A_BYTES, &tmA, full_bar(stage), kb * BLOCK_K,
-                      m_blk * BLOCK_M);
+          if (CG == 2) tma_load_2d_pair(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
+          else         tma_load_2d(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FP8, BLOCK_M, BN);
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(FP8, BLOCK_M * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = worker; t < total_tiles; t += num_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogues (both CTAs) drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -504,13 +519,21 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             const uint64_t koff = static_cast<uint64_t>(k * (UMMA_K >> 4));
-            if (FP8) mma_f8(d_tmem, adesc + koff, bdesc + koff, idesc, (kb | k) != 0);
-            else     mma_i8(d_tmem, adesc + koff, bdesc + koff, idesc, (kb | k) != 0);
+            const uint32_t accum = (kb | k) != 0;
+            if (CG == 2) {
+              if (FP8) mma_f8_pair(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
+              else     mma_i8_pair(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
+            } else {
+              if (FP8) mma_f8(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
+              else     mma_i8(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
+            }
           }
-          mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs) once these MMAs retire
+          if (CG == 2) mma_commit_pair(empty_bar(stage), 3); else mma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps of both CTAs
+        if (CG == 2) mma_commit_pair(tfull_bar(acc), 3); else mma_commit(tfull_bar(acc));
       }
     }
   } else {
@@ -520,7 +543,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int warps_total = NUM_EPI_WARPS * gridDim.x;
       for (int row = ew * gridDim.x + blockIdx.x; row < p.M; row += warps_total) {
         const float s = quantize_row_any<FP8>(p, row, lane);
-        if (lane == 0 && p.act_mode == ASQ_ACT_PER_TOKEN) {
+        if (lane == 0 && (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN)) {
           p.row_scale[row] = s;
           if (p.row_scale_out != nullptr) p.row_scale_out[row] = s;
         }
@@ -536,17 +559,19 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int half = ew >> 2;           // which half of the BN columns
     constexpr int CHUNKS = BN / 2 / 32; // 32-column chunks per warp
+    const uint32_t tempty_leader0 = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t tempty_leader1 = (CG == 2) ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = worker; t < total_tiles; t += num_workers, ++it) {
       int m_blk, n_blk;
       tile_coords(t, p, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const int row = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quad * 32 + lane;
       float rs = 0.f;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (p.act_mode == ASQ_ACT_PER_TOKEN && p.epi_kind == EPI_DEQUANT && row < p.M)
+      if ((p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) && p.epi_kind == EPI_DEQUANT && row < p.M)
         rs = __ldcg(p.row_scale + row);
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch) {
@@ -558,22 +583,26 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        else         mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (fused && threadIdx.x == 0) {
     // last CTA out restores the phase counters so the workspace is reusable by the next launch
     __threadfence();
     const uint32_t done = atomicAdd(p.sync + SYNC_EXIT, 1u);
     if (done == gridDim.x - 1) {
-      for (int i = 0; i < p.num_m_blocks; ++i) p.sync[1 + i] = 0u;
+      const int panels = (p.M + BLOCK_M - 1) / BLOCK_M;
+      for (int i = 0; i < panels; ++i) p.sync[1 + i] = 0u;
       p.sync[SYNC_EXIT] = 0u;
       __threadfence();
     }
@@ -688,17 +717,41 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
   return kSyncBytes + rs + aq;
 }
 
-template <bool FP8, int BN>
-int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const asq::LinearParams& p, int grid,
+template <bool FP8, int BN, int CG>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const asq::LinearParams& p, int workers,
                cudaStream_t stream) {
-  using Cfg = asq::TileCfg<BN>;
-  auto kern = asq::asq_linear_kernel<FP8, BN>;
+  using Cfg = asq::TileCfg<BN, CG>;
+  auto kern = asq::asq_linear_kernel<FP8, BN, CG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  kern<<<grid, asq::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG), 1, 1);
+  cfg.blockDim = dim3(asq::NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
+}
+
+// Tile shape selection.  CTA pairs (256-row tiles) whenever there are at least two 128-row panels; the
+// accumulator width follows N.  ASQ_FORCE_CG=1|2 overrides the pairing (profiling / tests).
+int pick_cta_group(int64_t M) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("ASQ_FORCE_CG");
+    forced = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+  }
+  if (forced) return forced;
+  return M > asq::BLOCK_M ? 2 : 1;
 }
 
 // Shared launcher: `a8` is the 8-bit A matrix TMA reads (caller's matrix, or the workspace copy).
@@ -710,8 +763,10 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   if (!st->supported)
     return fail(ASQ_ERR_CUDA, "device %d is not compute capability 10.0 (sm_100a kernels only)", dev);
 
+  const int cg = pick_cta_group(p.M);
   const int bn = (p.N > 128) ? 256 : (p.N > 64 ? 128 : 64);
-  p.num_m_blocks = (p.M + asq::BLOCK_M - 1) / asq::BLOCK_M;
+  const int tile_m = asq::BLOCK_M * cg;
+  p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
   p.num_n_blocks = (p.N + bn - 1) / bn;
   p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
   {  // keep one group's W tiles (group_n * bn * K bytes) within ~48 MB of the 126 MB L2
@@ -720,22 +775,23 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     p.group_n = static_cast<int>(gn < 1 ? 1 : (gn > p.num_n_blocks ? p.num_n_blocks : gn));
   }
   const long long tiles = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
-  const int grid = static_cast<int>(tiles < st->sm_count ? tiles : st->sm_count);
+  const int max_workers = st->sm_count / cg;
+  const int workers = static_cast<int>(tiles < max_workers ? tiles : max_workers);
 
   CUtensorMap tmA, tmB;
   rc = make_tmap(&tmA, a8, p.M, p.K, asq::BLOCK_M);
   if (rc != ASQ_OK) return rc;
-  rc = make_tmap(&tmB, w, p.N, p.K, bn);
+  rc = make_tmap(&tmB, w, p.N, p.K, bn / cg);
   if (rc != ASQ_OK) return rc;
 
+#define ASQ_DISPATCH(F8, BNV, CGV) return launch_cfg<F8, BNV, CGV>(tmA, tmB, p, workers, stream)
   if (fp8) {
-    if (bn == 256) return launch_cfg<true, 256>(tmA, tmB, p, grid, stream);
-    if (bn == 128) return launch_cfg<true, 128>(tmA, tmB, p, grid, stream);
-    return launch_cfg<true, 64>(tmA, tmB, p, grid, stream);
+    if (cg == 2) { if (bn == 256) ASQ_DISPATCH(true, 256, 2); if (bn == 128) ASQ_DISPATCH(true, 128, 2); ASQ_DISPATCH(true, 64, 2); }
+    if (bn == 256) ASQ_DISPATCH(true, 256, 1); if (bn == 128) ASQ_DISPATCH(true, 128, 1); ASQ_DISPATCH(true, 64, 1);
   }
-  if (bn == 256) return launch_cfg<false, 256>(tmA, tmB, p, grid, stream);
-  if (bn == 128) return launch_cfg<false, 128>(tmA, tmB, p, grid, stream);
-  return launch_cfg<false, 64>(tmA, tmB, p, grid, stream);
+  if (cg == 2) { if (bn == 256) ASQ_DISPATCH(false, 256, 2); if (bn == 128) ASQ_DISPATCH(false, 128, 2); ASQ_DISPATCH(false, 64, 2); }
+  if (bn == 256) ASQ_DISPATCH(false, 256, 1); if (bn == 128) ASQ_DISPATCH(false, 128, 1); ASQ_DISPATCH(false, 64, 1);
+#undef ASQ_DISPATCH
 }
 
 int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {
@@ -762,8 +818,11 @@ int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const floa
   if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
   if (act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC)
     return fail(ASQ_ERR_UNSUPPORTED, "per-tensor dynamic activation scale is not implemented in the fused kernel");
-  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN)
+  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN &&
+      act_mode != ASQ_ACT_ROW_SCALE_GIVEN)
     return fail(ASQ_ERR_INVALID, "bad act_mode %d", act_mode);
+  if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN && row_scale_out == nullptr && M > 0)
+    return fail(ASQ_ERR_INVALID, "ASQ_ACT_ROW_SCALE_GIVEN needs the [M] row scales in row_scale");
   if (fp8 && act_mode == ASQ_ACT_ROUND) return fail(ASQ_ERR_INVALID, "ASQ_ACT_ROUND is int8-only");
   if (M == 0) return ASQ_OK;
   if ((M + asq::BLOCK_M - 1) / asq::BLOCK_M + 1 > static_cast<int64_t>(kSyncBytes / 4))
@@ -776,7 +835,9 @@ int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const floa
   ws_layout(M, K, workspace, &ws);
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
-  p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.row_scale_out = row_scale_out; p.sync = ws.sync;
+  p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.sync = ws.sync;
+  if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN) p.row_scale_in = row_scale_out;  // in: caller-supplied scales
+  else p.row_scale_out = row_scale_out;
   p.quant_scale = quant_scale; p.inv_quant_scale = 1.0f / quant_scale;
   p.qmax = fp8 ? 448.0f : 127.0f; p.inv_qmax = 1.0f / p.qmax;
   p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
@@ -818,7 +879,7 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
                    int64_t M, int64_t N, int64_t K, int act_mode, float in_scale, float w_scale,
                    float* row_scale_out, int div_mode, void* workspace, size_t workspace_bytes, void* stream) {
   // per-token: y = acc * (w_scale * s[m]); static: y = acc * (w_scale * in_scale)
-  const float ds = (act_mode == ASQ_ACT_PER_TOKEN) ? w_scale : w_scale * in_scale;
+  const float ds = (act_mode == ASQ_ACT_PER_TOKEN || act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? w_scale : w_scale * in_scale;
   return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, in_scale, ds, nullptr,
                       row_scale_out, div_mode, workspace, workspace_bytes, stream);
 }
@@ -852,11 +913,13 @@ int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale, int6
                      float quant_scale, int div_mode, int fp8, void* stream) {
   if (M < 0 || K <= 0 || K % 16 != 0) return fail(ASQ_ERR_INVALID, "bad shape M=%lld K=%lld (K %% 16 == 0 required)", (long long)M, (long long)K);
   if (!is_float_dtype(x_dtype)) return fail(ASQ_ERR_INVALID, "x dtype must be f32, f16 or bf16");
-  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN)
+  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN &&
+      act_mode != ASQ_ACT_ROW_SCALE_GIVEN)
     return fail(act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC ? ASQ_ERR_UNSUPPORTED : ASQ_ERR_INVALID, "unsupported act_mode %d", act_mode);
   if (M == 0) return ASQ_OK;
   if (x == nullptr || q == nullptr) return fail(ASQ_ERR_INVALID, "null pointer argument");
-  if (act_mode == ASQ_ACT_PER_TOKEN && row_scale == nullptr) return fail(ASQ_ERR_INVALID, "row_scale required for per-token");
+  if ((act_mode == ASQ_ACT_PER_TOKEN || act_mode == ASQ_ACT_ROW_SCALE_GIVEN) && row_scale == nullptr)
+    return fail(ASQ_ERR_INVALID, "row_scale required for per-token modes");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(q) & 15))
     return fail(ASQ_ERR_INVALID, "x and q must be 16-byte aligned");
   int dev;
@@ -865,7 +928,9 @@ int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale, int6
   if (rc != ASQ_OK) return rc;
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
-  p.x = x; p.a_q = static_cast<uint8_t*>(q); p.row_scale = row_scale;
+  p.x = x; p.a_q = static_cast<uint8_t*>(q);
+  if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN) p.row_scale_in = row_scale;  // input: scales to quantise with
+  else p.row_scale = row_scale;
   p.quant_scale = quant_scale; p.inv_quant_scale = 1.0f / quant_scale;
   p.qmax = fp8 ? 448.0f : 127.0f; p.inv_qmax = 1.0f / p.qmax;
   p.M = static_cast<int>(M); p.K = static_cast<int>(K);

@@ -1,0 +1,202 @@
+"""Minimal Llama-style decoder stack used to measure the W8A8 linear path at model level.
+
+This is measurement plumbing, not a model zoo: the reference's model classes subclass HF
+transformers 4.42 internals that no longer exist in the installed transformers, so the
+benchmark needs its own thin stack.  Every projection is one of the reference-API modules from
+``autosmoothquant_b200.layers.nn.linear`` chosen from a ``quant_config`` dict exactly as the
+reference's ``autosmoothquant/models/llama.py:74-106,185-214`` does, with the norm-weight folding
+of ``llama.py:27-37,326-339``; everything that is not a quantized linear (embedding, RMSNorm,
+RoPE, attention, SiLU, lm_head) is ordinary torch and is reported separately from the INT8 work.
+
+Weights are synthetic (seeded normal, true shapes), converted with the modules' own
+``from_float`` (the reference's absmax weight quantiser).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .layers.nn.linear import (
+    FP8LinearDynamic,
+    W8A8BFP32OFP32Linear,
+    W8A8BFP32OFP32LinearWithQuantScale,
+)
+
+
+@dataclass(frozen=True)
+class DecoderConfig:
+    name: str
+    hidden: int
+    intermediate: int
+    layers: int
+    heads: int
+    kv_heads: int
+    vocab: int = 32000
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+    def linear_macs_per_token_per_layer(self) -> int:
+        kv = self.kv_heads * self.head_dim
+        return 2 * self.hidden * self.hidden + 2 * self.hidden * kv + 3 * self.hidden * self.intermediate
+
+
+LLAMA2_7B = DecoderConfig("llama-2-7b", 4096, 11008, 32, 32, 32)
+LLAMA2_13B = DecoderConfig("llama-2-13b", 5120, 13824, 40, 40, 40)
+LLAMA2_70B = DecoderConfig("llama-2-70b", 8192, 28672, 80, 64, 8)
+TINY = DecoderConfig("tiny", 256, 512, 2, 4, 4, vocab=512)
+CONFIGS = {c.name: c for c in (LLAMA2_7B, LLAMA2_13B, LLAMA2_70B, TINY)}
+
+DEFAULT_QUANT_CONFIG = {"qkv": "per-tensor", "out": "per-tensor", "fc1": "per-tensor", "fc2": "per-tensor",
+                        "type": "int8"}
+
+# synthetic calibration results (activation absmax / 127) for seeded N(0, 0.02) weights
+SYNTH_INPUT_SCALES = {"attn_input": 4.5 / 127, "out_input": 6.0 / 127, "gate_input": 4.5 / 127, "down_input": 8.0 / 127}
+
+
+def normalise_quant_config(cfg: Dict[str, str]) -> Dict[str, str]:
+    """quant_config.json semantics (reference README.md:25-41, smoothquant_model.py:62-70):
+    'fp8' is shorthand for 'fp8_e4m3'; fp8 needs an activation_scheme (default dynamic)."""
+    out = dict(DEFAULT_QUANT_CONFIG)
+    out.update(cfg or {})
+    if out["type"] == "fp8":
+        out["type"] = "fp8_e4m3"
+    if out["type"] not in ("int8", "fp8_e4m3"):
+        raise ValueError(f"unsupported quant type {out['type']!r}")
+    if out["type"] == "fp8_e4m3":
+        out.setdefault("activation_scheme", "dynamic")
+    for key in ("qkv", "out", "fc1", "fc2"):
+        if out[key] not in ("per-tensor", "per-token"):
+            raise ValueError(f"{key} must be per-tensor or per-token")
+    return out
+
+
+def _rand_linear(in_f: int, out_f: int, gen: torch.Generator, device, std: float = 0.02) -> nn.Linear:
+    lin = nn.Linear(in_f, out_f, bias=False, device=device, dtype=torch.float32)
+    with torch.no_grad():
+        lin.weight.normal_(0.0, std, generator=gen)
+    return lin
+
+
+def _make_proj(kind: str, in_f: int, out_f: int, qcfg: Dict[str, str], input_scale: float, gen, device) -> nn.Module:
+    """kind in {'qkv','out','fc1','fc2'} -> module class as llama.py:74-106,185-214 picks it."""
+    lin = _rand_linear(in_f, out_f, gen, device)
+    gran = qcfg[kind]
+    if qcfg["type"] == "fp8_e4m3":
+        mod = FP8LinearDynamic.from_float(lin, 1.0, act_quant="per-token")
+    elif kind in ("qkv", "fc1"):
+        mod = W8A8BFP32OFP32Linear.from_float(lin, input_scale, save_device=device, act_quant=gran)
+    else:
+        mod = W8A8BFP32OFP32LinearWithQuantScale.from_float(lin, input_scale, save_device=device, act_quant=gran)
+    del lin
+    return mod.to(device) if qcfg["type"] != "fp8_e4m3" else mod._apply(lambda t: t.to(device))
+
+
+def _rope_tables(seq: int, head_dim: int, theta: float, device, dtype):
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device, dtype=torch.float32) / head_dim))
+    ang = torch.outer(torch.arange(seq, device=device, dtype=torch.float32), inv)
+    emb = torch.cat((ang, ang), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def _apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    half = x.shape[-1] // 2
+    rot = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
+    return x * cos + rot * sin
+
+
+class QuantDecoderLayer(nn.Module):
+    def __init__(self, cfg: DecoderConfig, qcfg: Dict[str, str], gen, device, dtype):
+        super().__init__()
+        self.cfg = cfg
+        h, kv, inter = cfg.hidden, cfg.kv_heads * cfg.head_dim, cfg.intermediate
+        s = SYNTH_INPUT_SCALES
+        self.q_proj = _make_proj("qkv", h, h, qcfg, s["attn_input"], gen, device)
+        self.k_proj = _make_proj("qkv", h, kv, qcfg, s["attn_input"], gen, device)
+        self.v_proj = _make_proj("qkv", h, kv, qcfg, s["attn_input"], gen, device)
+        self.o_proj = _make_proj("out", h, h, qcfg, s["out_input"], gen, device)
+        self.gate_proj = _make_proj("fc1", h, inter, qcfg, s["gate_input"], gen, device)
+        self.up_proj = _make_proj("fc1", h, inter, qcfg, s["gate_input"], gen, device)
+        self.down_proj = _make_proj("fc2", inter, h, qcfg, s["down_input"], gen, device)
+        ln1 = torch.ones(h, dtype=torch.float32, device=device)
+        ln2 = torch.ones(h, dtype=torch.float32, device=device)
+        int8 = qcfg["type"] == "int8"
+        # fold 1/input_scale into the norm weight when the consumer is per-tensor (llama.py:326-339)
+        if int8 and qcfg["qkv"] == "per-tensor":
+            ln1 = ln1 / s["attn_input"]
+        if int8 and qcfg["fc1"] == "per-tensor":
+            ln2 = ln2 / s["gate_input"]
+        self.register_buffer("input_layernorm_weight", ln1.to(dtype))
+        self.register_buffer("post_attention_layernorm_weight", ln2.to(dtype))
+
+    def linears(self):
+        return [self.q_proj, self.k_proj, self.v_proj, self.o_proj, self.gate_proj, self.up_proj, self.down_proj]
+
+    def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+        cfg = self.cfg
+        B, S, H = x.shape
+        h = F.rms_norm(x, (H,), self.input_layernorm_weight, cfg.rms_eps)
+        # head counts are inferred from the projection width so tensor-parallel shards (heads / p) work too
+        q = self.q_proj(h).view(B, S, -1, cfg.head_dim).transpose(1, 2)
+        k = self.k_proj(h).view(B, S, -1, cfg.head_dim).transpose(1, 2)
+        v = self.v_proj(h).view(B, S, -1, cfg.head_dim).transpose(1, 2)
+        q, k = _apply_rope(q, cos, sin), _apply_rope(k, cos, sin)
+        attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=k.shape[1] != q.shape[1])
+        x = x + self.o_proj(attn.transpose(1, 2).reshape(B, S, -1))
+        h = F.rms_norm(x, (H,), self.post_attention_layernorm_weight, cfg.rms_eps)
+        x = x + self.down_proj(F.silu(self.gate_proj(h)) * self.up_proj(h))
+        return x
+
+
+class QuantDecoder(nn.Module):
+    """Embedding -> N quantized decoder layers -> norm -> lm_head (bf16, not quantized, as in the reference)."""
+
+    def __init__(self, cfg: DecoderConfig, quant_config: Optional[Dict[str, str]] = None, device="cuda",
+                 dtype=torch.bfloat16, seed: int = 0, layers: Optional[int] = None):
+        super().__init__()
+        self.cfg = cfg
+        self.qcfg = normalise_quant_config(quant_config or {})
+        self.dtype = dtype
+        gen = torch.Generator(device=device).manual_seed(seed)
+        n_layers = cfg.layers if layers is None else layers
+        self.embed = nn.Embedding(cfg.vocab, cfg.hidden, device=device, dtype=dtype)
+        with torch.no_grad():
+            self.embed.weight.normal_(0.0, 1.0, generator=gen)
+        self.layers = nn.ModuleList(QuantDecoderLayer(cfg, self.qcfg, gen, device, dtype) for _ in range(n_layers))
+        self.register_buffer("norm_weight", torch.ones(cfg.hidden, dtype=dtype, device=device))
+        self.lm_head = nn.Linear(cfg.hidden, cfg.vocab, bias=False, device=device, dtype=dtype)
+        with torch.no_grad():
+            self.lm_head.weight.normal_(0.0, 0.02, generator=gen)
+        self._rope = None
+
+    def quantized_linears(self):
+        return [m for layer in self.layers for m in layer.linears()]
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, last_token_only: bool = True) -> torch.Tensor:
+        B, S = input_ids.shape
+        if self._rope is None or self._rope[0] != S:
+            cos, sin = _rope_tables(S, self.cfg.head_dim, self.cfg.rope_theta, input_ids.device, self.dtype)
+            self._rope = (S, cos, sin)
+        _, cos, sin = self._rope
+        x = self.embed(input_ids)
+        for layer in self.layers:
+            x = layer(x, cos, sin)
+        if last_token_only:
+            x = x[:, -1:, :]
+        x = F.rms_norm(x, (self.cfg.hidden,), self.norm_weight, self.cfg.rms_eps)
+        return self.lm_head(x).float()
+
+
+def quantized_linear_ops(cfg: DecoderConfig, tokens: int, layers: Optional[int] = None) -> float:
+    """Algorithmic INT8 ops (2*MACs) of the quantized linears for `tokens` tokens."""
+    n_layers = cfg.layers if layers is None else layers
+    return 2.0 * cfg.linear_macs_per_token_per_layer() * n_layers * tokens

@@ -1,0 +1,196 @@
+"""Tensor parallelism for the quantized linears (Megatron layout, one process per GPU).
+
+The reference has no parallelism at all; BASELINE configs 4-5 shard qkv / fc1
+column-wise (split N: replicated input, no communication) and out / fc2 row-wise (split K: each
+rank multiplies its slice of the activation by its slice of the weight, partial [M,N] products are
+summed with ONE all-reduce over NCCL / NVLink).  The weight scale is per-tensor, so every shard
+keeps the full module's ``dequant_scale``; the fp32 bias is added by rank 0's shard only.
+
+Row-parallel + per-token: the reference semantics need the row absmax over the WHOLE K, so the
+local per-token scales (monotonic in the local absmax) are max-all-reduced first and the kernel
+quantises with the supplied scales (``ASQ_ACT_ROW_SCALE_GIVEN``); ``local_scales=True`` skips that
+exchange (each rank dequantises with its own scale: valid, slightly more accurate, not bit-identical
+to the single-GPU reference).
+
+``reduce="int32"`` is the exactness mode used by the tests: the int32 accumulators are all-reduced
+and dequantised afterwards, which is bit-identical to the unsharded module.
+
+Compute is injectable (``backend``) so the host-side logic is testable on CPU with gloo and the
+oracle; the default backend is the CUDA library and has no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib
+from .layers.nn.linear import (
+    W8A8BFP32OFP32Linear,
+    W8A8BFP32OFP32LinearWithQuantScale,
+)
+
+
+def _shard_bounds(size: int, rank: int, world: int, align: int = 16):
+    if size % (world * align) != 0:
+        raise ValueError(f"dimension {size} is not divisible by world {world} x {align}")
+    step = size // world
+    return rank * step, (rank + 1) * step
+
+
+def shard_column(module: nn.Module, rank: int, world: int) -> nn.Module:
+    """Rank's column-parallel shard (rows [rN/p, (r+1)N/p) of the [N,K] weight) of an INT8 module."""
+    lo, hi = _shard_bounds(module.out_features, rank, world, align=1)
+    out = type(module)(module.in_features, hi - lo, module.use_bias, module.act_quant)
+    out.weight = module.weight[lo:hi].contiguous()
+    if module.use_bias:
+        out.bias = module.bias[lo:hi].contiguous()
+    for name in module._scale_names:
+        setattr(out, name, getattr(module, name).clone())
+    return out
+
+
+def shard_row(module: nn.Module, rank: int, world: int) -> nn.Module:
+    """Rank's row-parallel shard (columns [rK/p, (r+1)K/p) of the [N,K] weight); bias stays on rank 0."""
+    lo, hi = _shard_bounds(module.in_features, rank, world, align=16)
+    keep_bias = module.use_bias and rank == 0
+    out = type(module)(hi - lo, module.out_features, keep_bias, module.act_quant)
+    out.weight = module.weight[:, lo:hi].contiguous()
+    if keep_bias:
+        out.bias = module.bias.clone()
+    for name in module._scale_names:
+        setattr(out, name, getattr(module, name).clone())
+    return out
+
+
+# ------------------------------------------------------------------------------ compute backends
+class CudaBackend:
+    """The product path: fused kernels through the C ABI."""
+
+    @staticmethod
+    def linear(module, x2, mode, quant_scale, row_scale=None):
+        return _lib.w8a8_linear(x2, module.weight, module.bias if module.use_bias else None, mode, quant_scale,
+                                float(module.dequant_scale.item()), row_scale_out=row_scale)
+
+    @staticmethod
+    def local_row_scales(x2):
+        _, s = _lib.quantize_act(x2, _lib.ACT_PER_TOKEN)
+        return s
+
+    @staticmethod
+    def int32_partial(module, x2, mode, quant_scale, row_scale=None):
+        if mode == _lib.ACT_PER_TOKEN:
+            raise NotImplementedError("int32 reduction needs global row scales (local_scales=False)")
+        q, _ = _lib.quantize_act(x2, mode, quant_scale, row_scale=row_scale)
+        acc = torch.empty((x2.shape[0], module.out_features), dtype=torch.int32, device=x2.device)
+        _lib.i8gemm_o32(q, module.weight, acc)
+        return acc
+
+
+class ColumnParallelLinear(nn.Module):
+    """qkv / fc1: every rank holds N/p output features; input replicated, output stays sharded."""
+
+    def __init__(self, shard: nn.Module, backend=CudaBackend):
+        super().__init__()
+        self.shard = shard
+        self.backend = backend
+        self.in_features, self.out_features = shard.in_features, shard.out_features
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.shard
+        x2 = x.reshape(-1, m.in_features)
+        if m.act_quant == "per-token":
+            mode, qs = _lib.ACT_PER_TOKEN, 1.0
+        elif isinstance(m, W8A8BFP32OFP32LinearWithQuantScale):
+            mode, qs = _lib.ACT_SCALE, float(m.quant_scale.item())
+        else:
+            mode, qs = _lib.ACT_ROUND, 1.0
+        y = self.backend.linear(m, x2, mode, qs)
+        return y.view(*x.shape[:-1], m.out_features)
+
+
+class RowParallelLinear(nn.Module):
+    """out / fc2: every rank holds K/p input features; partial outputs are all-reduced (sum).
+
+    ``has_bias`` tells every rank whether the unsharded module had a bias (only rank 0's shard keeps it).
+    """
+
+    def __init__(self, shard: nn.Module, group=None, reduce: str = "native", local_scales: bool = False,
+                 backend=CudaBackend, has_bias: Optional[bool] = None):
+        super().__init__()
+        if reduce not in ("native", "fp32", "int32"):
+            raise ValueError("reduce must be 'native' (activation dtype), 'fp32' or 'int32'")
+        self.shard, self.group, self.reduce, self.local_scales, self.backend = shard, group, reduce, local_scales, backend
+        self.has_bias = shard.use_bias if has_bias is None else has_bias
+        self.in_features, self.out_features = shard.in_features, shard.out_features
+        self._full_bias = None
+
+    def _bias_everywhere(self, device) -> Optional[torch.Tensor]:
+        """int32 mode dequantises after the reduction on every rank, so every rank needs the bias."""
+        if not self.has_bias:
+            return None
+        if self._full_bias is None:
+            b = (self.shard.bias.clone().to(device) if self.shard.use_bias
+                 else torch.zeros(self.out_features, dtype=torch.float32, device=device))
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)  # only rank 0 contributes non-zeros
+            self._full_bias = b
+        return self._full_bias
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.shard
+        x2 = x.reshape(-1, m.in_features)
+        row_scale = None
+        if m.act_quant == "per-token":
+            if self.local_scales:
+                mode, qs = _lib.ACT_PER_TOKEN, 1.0
+            else:
+                row_scale = self.backend.local_row_scales(x2)
+                dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)  # = scale of the global row absmax
+                mode, qs = _lib.ACT_ROW_SCALE_GIVEN, 1.0
+        elif isinstance(m, W8A8BFP32OFP32LinearWithQuantScale):
+            mode, qs = _lib.ACT_SCALE, float(m.quant_scale.item())
+        else:
+            mode, qs = _lib.ACT_ROUND, 1.0
+
+        if self.reduce == "int32":
+            # exactness mode: sum the integer accumulators, then the unsharded module's fp32 epilogue
+            acc = self.backend.int32_partial(m, x2, mode, qs, row_scale)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+            ds = float(m.dequant_scale.item())
+            y = (ds * row_scale.view(-1, 1)) * acc if row_scale is not None else ds * acc
+            bias = self._bias_everywhere(y.device)
+            if bias is not None:
+                y = y + bias
+            return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
+
+        y = self.backend.linear(m, x2, mode, qs, row_scale)
+        if self.reduce == "fp32" and y.dtype != torch.float32:
+            y = y.float()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+        return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
+
+
+def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: Optional[Dict[str, str]] = None,
+                     group=None, dtype=torch.bfloat16, seed: int = 0):
+    """The benchmark stack of ``harness.QuantDecoder`` with every projection tensor-parallel: q/k/v/gate/up
+    column-sharded, o/down row-sharded (+ all-reduce), attention over the local heads."""
+    from . import harness
+
+    model = harness.QuantDecoder(cfg, quant_config, device=device, dtype=dtype, seed=seed, layers=layers)
+    if model.qcfg["type"] != "int8":
+        raise NotImplementedError("tensor-parallel fp8 stack")
+    for layer in model.layers:
+        for name in ("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj"):
+            full = getattr(layer, name)
+            setattr(layer, name, ColumnParallelLinear(shard_column(full, rank, world).to(device)))
+        for name in ("o_proj", "down_proj"):
+            full = getattr(layer, name)
+            setattr(layer, name, RowParallelLinear(shard_row(full, rank, world).to(device), group=group,
+                                                   has_bias=full.use_bias))
+        layer.tp_world = world
+    model.tp_world = world
+    return model

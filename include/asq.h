@@ -9,7 +9,7 @@
  * Reference interfaces replaced (paths relative to the reference repo):
  *   - csrc/int8gemm/bindings.cpp:69-84   I8CUGEMM::linear_a8_w8_o32_   -> asq_i8gemm_o32
  *   - csrc/int8gemm/bindings.cpp:52-67   I8CUGEMM::linear_a8_w8_o32    -> asq_i8gemm_o32
- *   - csrc/int8gemm/bindings.cpp:86-142  linear_a8_w8_o8[_], _b8_o8_   -> asq_i8gemm_o8
+ *   - csrc/int8gemm/bindings.cpp:86-142  linear_a8_w8_o8[_], _b8_o8_   -> asq_i8gemm_epi
  *   - autosmoothquant/layers/nn/linear.py:83-106   W8A8BFP32OFP32Linear.forward
  *   - autosmoothquant/layers/nn/linear.py:172-208  W8A8BFP32OFP32QKVLinear.forward
  *   - autosmoothquant/layers/nn/linear.py:278-302  ...LinearWithQuantScale.forward
@@ -73,7 +73,9 @@ typedef enum asq_act_mode {
   ASQ_ACT_ROUND = 0,
   ASQ_ACT_SCALE = 1,
   ASQ_ACT_PER_TOKEN = 2,
-  ASQ_ACT_PER_TENSOR_DYNAMIC = 3
+  ASQ_ACT_PER_TENSOR_DYNAMIC = 3,
+  ASQ_ACT_ROW_SCALE_GIVEN = 4 /* per-token arithmetic with caller-supplied scales s[m] (row-parallel
+                                 tensor parallelism: the global row absmax is all-reduced first) */
 } asq_act_mode;
 
 /* How `tensor / python_scalar` is evaluated.  torch on CUDA multiplies by the
@@ -109,7 +111,8 @@ size_t asq_workspace_bytes(int64_t M, int64_t K);
  *   dequant_scale   scalar applied to every column, used when col_scale == NULL
  *   col_scale [N] fp32 or NULL: per-output-column dequant scale (the QKV variant's
  *             piecewise-constant q/k/v scales, linear.py:197-200)
- *   row_scale_out [M] fp32 or NULL: receives the per-token scales (ASQ_ACT_PER_TOKEN)
+ *   row_scale_out [M] fp32 or NULL: receives the per-token scales (ASQ_ACT_PER_TOKEN); with
+ *             ASQ_ACT_ROW_SCALE_GIVEN it is an INPUT holding the scales to quantise with
  * Arithmetic (bit-exact with the reference's fp32 epilogue):
  *   f = col_scale ? col_scale[n] : dequant_scale;  per-token: f = f * s[m]
  *   y[m,n] = T( f * f32(acc[m,n]) (+ bias[n]) )     acc = exact int32 dot product       */

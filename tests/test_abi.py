@@ -1,0 +1,72 @@
+"""The C-ABI library loads without a GPU and exports exactly what include/asq.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from autosmoothquant_b200 import _lib, build
+
+    build.build()  # no-op when the in-tree .so is newer than its sources
+    return _lib.load()
+
+
+def declared_functions():
+    text = (ROOT / "include" / "asq.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(asq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(lib):
+    from autosmoothquant_b200 import _lib
+
+    assert declared_functions() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in declared_functions():
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr), name
+
+
+def test_no_torch_or_cublas_dependency():
+    """The boundary is a plain C ABI: the .so must not link torch, cuBLAS or CUTLASS-built libraries."""
+    import subprocess
+
+    from autosmoothquant_b200 import _lib
+
+    out = subprocess.run(["ldd", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for forbidden in ("libtorch", "libc10", "libcublas", "libcudnn", "libpython"):
+        assert forbidden not in out, out
+
+
+def test_version_and_workspace(lib):
+    assert lib.asq_version() == 100
+    small = lib.asq_workspace_bytes(1, 16)
+    big = lib.asq_workspace_bytes(2048, 4096)
+    assert big >= 2048 * 4096 + 2048 * 4 and small >= 16 and big % 1024 == 0
+
+
+def test_argument_validation_happens_before_any_device_work(lib):
+    """Bad arguments are reported as ASQ_ERR_INVALID with a message, GPU or not."""
+    rc = lib.asq_i8gemm_o32(None, None, None, 4, 4, 24, None)  # K not a multiple of 16
+    assert rc == -1
+    assert b"multiple of 16" in lib.asq_last_error()
+    rc = lib.asq_quantize_act(None, 7, None, None, 4, 32, 0, ctypes.c_float(1.0), 0, 0, None)  # bad dtype
+    assert rc == -1
+
+
+def test_fails_loudly_without_a_device(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    buf = (ctypes.c_char * 4096)()
+    addr = (ctypes.addressof(buf) + 15) & ~15
+    rc = lib.asq_i8gemm_o32(addr, addr, addr, 16, 16, 16, None)
+    assert rc == -3  # ASQ_ERR_CUDA: no fallback
+    assert lib.asq_device_supported() == 0
