@@ -46,6 +46,15 @@ constexpr int SYNC_EXIT = 0;                          // sync[0]: CTAs that fini
 
 enum EpiKind : int { EPI_DEQUANT = 0, EPI_RAW_I32 = 1, EPI_ALPHA_BETA = 2 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// timeline slots (per CTA): 0 start, 1 setup done, 2 phase-1 done (warp 2), 3 first panel acquired,
+// 4 first full barrier passed (MMA), 5 first accumulator ready (epilogue), 6 last tile stored, 7 exit
+#define ASQ_STAMP(slot) do { if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + (slot)] = globaltimer_ns(); } while (0)
+
 struct LinearParams {
   // phase 1
   const void* x;         // nullptr: A is already 8-bit (tmA points at the caller's matrix)
@@ -63,7 +72,9 @@ struct LinearParams {
   float dequant_scale, alpha, beta;
   int M, N, K;
   int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
-  int num_m_blocks, num_n_blocks, num_k_blocks, group_n;
+  int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;
+  int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
+  unsigned long long* dbg;  // optional timeline buffer (8 slots per CTA), nullptr in production
 };
 
 // ------------------------------------------------------------------ element helpers
@@ -273,152 +284,176 @@ __device__ __forceinline__ float load_bias_any(const void* b, int dtype, int col
   return reinterpret_cast<const float*>(b)[col];
 }
 
-// One warp lane owns row `row`, 32 consecutive columns starting at col0; r[] = raw accumulators.
-template <bool FP8>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row, int col0, float rs,
-                                               const LinearParams& p) {
-  if (row >= p.M || col0 >= p.N) return;
-  const int N = p.N;
-  const int ncols = min(32, N - col0);
-  const size_t off = static_cast<size_t>(row) * N + col0;
-
-  if (p.epi_kind == EPI_RAW_I32) {
-    int32_t* dst = reinterpret_cast<int32_t*>(p.y) + off;
-    if (ncols == 32 && (N & 3) == 0) {
+// 32 consecutive fp32 values of a per-column vector starting at col0 (multiple of 32): vector loads when
+// the whole chunk is in range and the pointer is 16-byte aligned, guarded scalar loads otherwise.
+// Every index is a compile-time constant so the array stays in registers.
+__device__ __forceinline__ void load_cols32(const float* __restrict__ src, int col0, int N, float (&out)[32]) {
+  if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(src + col0) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src + col0);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    } else {
-      for (int j = 0; j < ncols; ++j) dst[j] = static_cast<int32_t>(r[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(s4 + j);
+      out[4 * j] = t.x; out[4 * j + 1] = t.y; out[4 * j + 2] = t.z; out[4 * j + 3] = t.w;
     }
-    return;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = (col0 + j < N) ? __ldg(src + col0 + j) : 0.f;
   }
+}
 
-  float v[32];
+// Raw accumulators r[32] (row `row`, columns col0..col0+31) -> fp32 results v[32] following the reference's
+// order of operations (linear.py:93,104 / :197-207): factor first, then * acc, then + bias, each a separate
+// fp32 rounding (no FMA contraction), so the result is bit-identical to eager torch.
+template <bool FP8>
+__device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (&v)[32], int col0, float rs,
+                                                const LinearParams& p) {
+  const int N = p.N;
   if (p.epi_kind == EPI_DEQUANT) {
-    // reference order of operations (linear.py:93,104 / :197-207): factor first, then * acc, then + bias,
-    // each a separate fp32 rounding (no FMA contraction) so the result is bit-identical to torch.
     const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN);
     const float f_scalar = per_token ? __fmul_rn(p.dequant_scale, rs) : p.dequant_scale;
+    if (p.col_scale != nullptr) {
+      float cs[32];
+      load_cols32(p.col_scale, col0, N, cs);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = col0 + j;
-      const float a = FP8 ? __uint_as_float(r[j]) : __int2float_rn(static_cast<int32_t>(r[j]));
-      float f = f_scalar;
-      if (p.col_scale != nullptr && j < ncols) {
-        f = __ldg(p.col_scale + c);
-        if (per_token) f = __fmul_rn(f, rs);
+      for (int j = 0; j < 32; ++j) {
+        const float a = FP8 ? __uint_as_float(r[j]) : __int2float_rn(static_cast<int32_t>(r[j]));
+        const float f = per_token ? __fmul_rn(cs[j], rs) : cs[j];
+        v[j] = __fmul_rn(f, a);
       }
-      float t = __fmul_rn(f, a);
-      if (p.bias != nullptr && j < ncols) t = __fadd_rn(t, __ldg(p.bias + c));
-      v[j] = t;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = FP8 ? __uint_as_float(r[j]) : __int2float_rn(static_cast<int32_t>(r[j]));
+        v[j] = __fmul_rn(f_scalar, a);
+      }
+    }
+    if (p.bias != nullptr) {
+      float b[32];
+      load_cols32(p.bias, col0, N, b);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(v[j], b[j]);
     }
   } else {  // EPI_ALPHA_BETA: v = alpha*acc + beta*bias  (cublasLt o8 / csrc/kernels/linear.cu epilogues)
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float a = __int2float_rn(static_cast<int32_t>(r[j]));
       float t = __fmul_rn(p.alpha, a);
-      if (p.bias_any != nullptr && j < ncols)
+      if (p.bias_any != nullptr && col0 + j < N)
         t = __fadd_rn(t, __fmul_rn(p.beta, load_bias_any(p.bias_any, p.bias_dtype, col0 + j)));
       if (p.flags & ASQ_EPI_RELU) t = fmaxf(t, 0.f);
       v[j] = t;
     }
   }
+}
 
-  switch (p.y_dtype) {
-    case ASQ_BF16:
-    case ASQ_F16: {
-      uint16_t* dst = reinterpret_cast<uint16_t*>(p.y) + off;
-      const bool bf = (p.y_dtype == ASQ_BF16);
-      if (ncols == 32 && (N & 7) == 0) {
+// 32 fp32 results -> packed output words of the requested type (w[] holds 32 * elem_size / 4 words).
+__device__ __forceinline__ void pack_out16(const float (&v)[32], uint32_t (&w)[16], bool bf) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 o;
-          o.x = bf ? pack_bf16x2(v[j], v[j + 1]) : pack_f16x2(v[j], v[j + 1]);
-          o.y = bf ? pack_bf16x2(v[j + 2], v[j + 3]) : pack_f16x2(v[j + 2], v[j + 3]);
-          o.z = bf ? pack_bf16x2(v[j + 4], v[j + 5]) : pack_f16x2(v[j + 4], v[j + 5]);
-          o.w = bf ? pack_bf16x2(v[j + 6], v[j + 7]) : pack_f16x2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(dst + j) = o;
-        }
-      } else {
-        for (int j = 0; j < ncols; ++j) {
-          uint32_t w = bf ? pack_bf16x2(v[j], 0.f) : pack_f16x2(v[j], 0.f);
-          dst[j] = static_cast<uint16_t>(w & 0xFFFFu);
-        }
-      }
-      break;
-    }
-    case ASQ_F32: {
-      float* dst = reinterpret_cast<float*>(p.y) + off;
-      if (ncols == 32 && (N & 3) == 0) {
+  for (int j = 0; j < 16; ++j) w[j] = bf ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : pack_f16x2(v[2 * j], v[2 * j + 1]);
+}
+
+// Fallback store (odd N, int8 output, ...): direct global writes, predicated per element.
+template <bool FP8>
+__device__ __forceinline__ void store_chunk_direct(const uint32_t (&r)[32], int row, int col0, float rs,
+                                                   const LinearParams& p) {
+  if (row >= p.M || col0 >= p.N) return;
+  const int N = p.N;
+  const size_t off = static_cast<size_t>(row) * N + col0;
+  if (p.epi_kind == EPI_RAW_I32) {
+    int32_t* dst = reinterpret_cast<int32_t*>(p.y) + off;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        for (int j = 0; j < ncols; ++j) dst[j] = v[j];
-      }
-      break;
-    }
-    case ASQ_I32: {
-      int32_t* dst = reinterpret_cast<int32_t*>(p.y) + off;
-      for (int j = 0; j < ncols; ++j) dst[j] = __float2int_rn(v[j]);
-      break;
-    }
-    case ASQ_I8: {
-      int8_t* dst = reinterpret_cast<int8_t*>(p.y) + off;
-      if (ncols == 32 && (N & 15) == 0) {
-        uint32_t w[8];
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < N) dst[j] = static_cast<int32_t>(r[j]);
+    return;
+  }
+  float v[32];
+  epilogue_values<FP8>(r, v, col0, rs, p);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          w[j] = cvt_s8(v[4 * j]) | (cvt_s8(v[4 * j + 1]) << 8) | (cvt_s8(v[4 * j + 2]) << 16) |
-                 (cvt_s8(v[4 * j + 3]) << 24);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-      } else {
-        for (int j = 0; j < ncols; ++j) dst[j] = static_cast<int8_t>(cvt_s8(v[j]));
+  for (int j = 0; j < 32; ++j) {
+    if (col0 + j < N) {
+      switch (p.y_dtype) {
+        case ASQ_BF16: reinterpret_cast<__nv_bfloat16*>(p.y)[off + j] = __float2bfloat16_rn(v[j]); break;
+        case ASQ_F16: reinterpret_cast<__half*>(p.y)[off + j] = __float2half_rn(v[j]); break;
+        case ASQ_F32: reinterpret_cast<float*>(p.y)[off + j] = v[j]; break;
+        case ASQ_I32: reinterpret_cast<int32_t*>(p.y)[off + j] = __float2int_rn(v[j]); break;
+        case ASQ_I8: reinterpret_cast<int8_t*>(p.y)[off + j] = static_cast<int8_t>(cvt_s8(v[j])); break;
+        default: break;
       }
-      break;
     }
-    default:
-      break;
+  }
+}
+
+// Staged store: this lane's 32 results go to row `lane` of the warp's 32-row x 128-byte staging tile in
+// shared memory, 16-byte chunks XOR-swizzled with (row & 7) exactly as CU_TENSOR_MAP_SWIZZLE_128B expects
+// (also makes the quarter-warp stores bank-conflict free); one elected lane then issues a TMA store, which
+// writes full 128-byte lines and clips rows >= M / columns >= N by itself.
+// `chunk16` = index of the first 16-byte chunk inside the 128-byte row (0 or 4 for 2-byte outputs).
+template <int NW>
+__device__ __forceinline__ void stage_words(uint32_t stage_base, int lane, int chunk16, const uint32_t (&w)[NW]) {
+#pragma unroll
+  for (int c = 0; c < NW / 4; ++c) {
+    const uint32_t addr = stage_base + lane * 128 + (((chunk16 + c) ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                 "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                 : "memory");
   }
 }
 
 // ------------------------------------------------------------------ tile schedule
-// Tiles are walked M-panel by M-panel with N fastest, inside groups of `group_n` N-blocks sized so one
-// group's W tiles stay L2-resident.  Walking panels in order lets the first wave start as soon as the
-// first panels of phase 1 exist while later panels are still being quantised.
+// Tile walk.  raster_m == 0: M-tile by M-tile with N fastest, inside groups of `group` N-blocks (one
+// group's W tiles stay L2-resident; the first wave only needs the first activation panels, so it can
+// start while phase 1 is still quantising later rows).  raster_m == 1: groups of `group` M-tiles with M
+// fastest inside a group (concurrent CTAs share W tiles).
 __device__ __forceinline__ void tile_coords(int t, const LinearParams& p, int& m_blk, int& n_blk) {
-  const int group_size = p.group_n * p.num_m_blocks;
-  const int g = t / group_size;
-  const int first_n = g * p.group_n;
-  const int gn = min(p.num_n_blocks - first_n, p.group_n);
-  const int local = t - g * group_size;
-  m_blk = local / gn;
-  n_blk = first_n + local % gn;
+  if (p.raster_m) {
+    const int group_size = p.group * p.num_n_blocks;
+    const int g = t / group_size;
+    const int first_m = g * p.group;
+    const int gm = min(p.num_m_blocks - first_m, p.group);
+    const int local = t - g * group_size;
+    m_blk = first_m + local % gm;
+    n_blk = local / gm;
+  } else {
+    const int group_size = p.group * p.num_m_blocks;
+    const int g = t / group_size;
+    const int first_n = g * p.group;
+    const int gn = min(p.num_n_blocks - first_n, p.group);
+    const int local = t - g * group_size;
+    m_blk = local / gn;
+    n_blk = first_n + local % gn;
+  }
 }
 
 // BN = accumulator width (UMMA N).  CG = CTAs per tile: 1 -> a 128 x BN tile per CTA; 2 -> a CTA pair
 // (cta_group::2) owns a 256 x BN tile: each CTA stages its own 128 A rows and HALF of the W tile, the
 // leader issues 256 x BN MMAs that read both CTAs' shared memory, each CTA drains its own 128 TMEM lanes.
 // Pairing halves the W bytes every SM pulls from L2 per MMA, which is what bounds 8-bit GEMMs here.
+constexpr uint32_t EPI_BUF_BYTES = 32 * 128;  // one warp's staging tile: 32 rows x 128 bytes
+constexpr uint32_t EPI_NBUF = 2;              // double-buffered per warp
+constexpr uint32_t EPI_BYTES = NUM_EPI_WARPS * EPI_BUF_BYTES * EPI_NBUF;
+constexpr uint32_t SMEM_LIMIT = 232448;       // 227 KB per CTA on sm_100
+
 template <int BN, int CG>
 struct TileCfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K;
   static constexpr uint32_t B_ROWS = BN / CG;  // W rows staged per CTA
   static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K;
-  static constexpr int STAGES = (192 * 1024) / (A_BYTES + B_BYTES) > 8 ? 8 : (192 * 1024) / (A_BYTES + B_BYTES);
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t BUDGET = SMEM_LIMIT - EPI_BYTES - 256 - 1024;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator
-  static constexpr uint32_t BAR_OFFSET = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;  // multiple of 1024
+  static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr uint32_t SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
   static constexpr int TILE_M = BLOCK_M * CG;
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 // ------------------------------------------------------------------ the kernel
 template <bool FP8, int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const LinearParams p) {
+                  const __grid_constant__ CUtensorMap tmY, const LinearParams p) {
   using Cfg = TileCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -442,6 +477,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int worker = blockIdx.x / CG;
   const int total_tiles = p.num_m_blocks * p.num_n_blocks;       // num_m_blocks counts TILE_M-row tiles
   const bool fused = (p.x != nullptr);
+  if (threadIdx.x == 0) ASQ_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -464,6 +500,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // peer barriers must exist before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) ASQ_STAMP(1);
 
   if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
@@ -490,6 +527,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             while (ld_acquire_gpu(flag) < need) __nanosleep(64);
             fence_proxy_async_all();  // phase-1 generic-proxy stores -> TMA (async proxy) reads
             panel_ready = true;
+            if (t == worker) ASQ_STAMP(3);
           }
           if (CG == 2) tma_load_2d_pair(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
           else         tma_load_2d(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
@@ -513,6 +551,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) ASQ_STAMP(4);
           const uint64_t adesc = make_smem_desc_sw128(base + stage * Cfg::A_BYTES);
           const uint64_t bdesc = make_smem_desc_sw128(base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES);
 #pragma unroll
@@ -549,11 +588,9 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         fence_proxy_async_all();
         __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          red_release_gpu_add(p.sync + 1 + row / BLOCK_M, 1u);
-        }
+        if (lane == 0) red_release_gpu_add(p.sync + 1 + row / BLOCK_M, 1u);  // release: orders the row's stores
       }
+      if (ew == 0 && lane == 0) ASQ_STAMP(2);
     }
     // ===================== phase 2: epilogue =====================
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
@@ -561,25 +598,97 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int CHUNKS = BN / 2 / 32; // 32-column chunks per warp
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
+    const uint32_t stage_base = base + Cfg::EPI_OFFSET + ew * (EPI_BUF_BYTES * EPI_NBUF);
+    const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
+    const bool staged = p.tma_store && (!out16 || CHUNKS >= 2);
+    const int elem = out16 ? 2 : 4;
+    uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     int it = 0;
     for (int t = worker; t < total_tiles; t += num_workers, ++it) {
       int m_blk, n_blk;
       tile_coords(t, p, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int row = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quad * 32 + lane;
+      const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quad * 32;
+      const int row = row0 + lane;
+      const int col_base = n_blk * BN + half * (BN / 2);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
       float rs = 0.f;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (it == 0 && ew == 0 && lane == 0) ASQ_STAMP(5);
       if ((p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) && p.epi_kind == EPI_DEQUANT && row < p.M)
         rs = __ldcg(p.row_scale + row);
+      if (staged && out16) {
+        // 64 output columns (two TMEM chunks) fill one 128-byte wide staging tile
 #pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ++ch) {
-        const int col_in_tile = half * (BN / 2) + ch * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_in_tile, r);
-        tmem_ld_wait();
-        epilogue_chunk<FP8>(r, row, n_blk * BN + col_in_tile, rs, p);
+        for (int g = 0; g < CHUNKS / 2; ++g) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + g * 64, r0);
+          tmem_ld_32x32(taddr + g * 64 + 32, r1);
+          const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+          if (gcount >= EPI_NBUF) {  // the store that last used this buffer must have read it
+            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          const int col0 = col_base + g * 64;
+          float v[32];
+          uint32_t w[16];
+          epilogue_values<FP8>(r0, v, col0, rs, p);
+          pack_out16(v, w, p.y_dtype == ASQ_BF16);
+          stage_words<16>(buf, lane, 0, w);
+          epilogue_values<FP8>(r1, v, col0 + 32, rs, p);
+          pack_out16(v, w, p.y_dtype == ASQ_BF16);
+          stage_words<16>(buf, lane, 4, w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && col0 < p.N) {
+            tma_store_2d(&tmY, buf, col0 * elem, row0);
+            tma_store_commit();
+          }
+          ++gcount;
+        }
+      } else if (staged) {
+        // 4-byte outputs: one TMEM chunk (32 columns) is one 128-byte wide staging tile
+#pragma unroll 1
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+          if (gcount >= EPI_NBUF) {
+            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          const int col0 = col_base + ch * 32;
+          if (p.epi_kind == EPI_RAW_I32) {
+            stage_words<32>(buf, lane, 0, r);
+          } else {
+            float v[32];
+            uint32_t w[32];
+            epilogue_values<FP8>(r, v, col0, rs, p);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              w[j] = (p.y_dtype == ASQ_I32) ? static_cast<uint32_t>(__float2int_rn(v[j])) : __float_as_uint(v[j]);
+            stage_words<32>(buf, lane, 0, w);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && col0 < p.N) {
+            tma_store_2d(&tmY, buf, col0 * elem, row0);
+            tma_store_commit();
+          }
+          ++gcount;
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          store_chunk_direct<FP8>(r, row, col_base + ch * 32, rs, p);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -588,6 +697,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else         mbar_arrive(tempty_bar(acc));
       }
     }
+    if (lane == 0) tma_store_wait_all();  // staged tiles fully written before the CTA retires
+    if (ew == 0 && lane == 0) ASQ_STAMP(6);
   }
 
   tc_fence_before();
@@ -596,6 +707,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (threadIdx.x == 0) ASQ_STAMP(7);
   if (fused && threadIdx.x == 0) {
     // last CTA out restores the phase counters so the workspace is reusable by the next launch
     __threadfence();
@@ -718,8 +830,8 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 }
 
 template <bool FP8, int BN, int CG>
-int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const asq::LinearParams& p, int workers,
-               cudaStream_t stream) {
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const asq::LinearParams& p,
+               int workers, cudaStream_t stream) {
   using Cfg = asq::TileCfg<BN, CG>;
   auto kern = asq::asq_linear_kernel<FP8, BN, CG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -737,7 +849,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const asq::Linear
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, p);
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
 }
@@ -763,16 +875,32 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   if (!st->supported)
     return fail(ASQ_ERR_CUDA, "device %d is not compute capability 10.0 (sm_100a kernels only)", dev);
 
+  {  // ASQ_DEBUG_TIMELINE=<device pointer, hex>: per-CTA phase timestamps (profiling builds of the caller)
+    const char* e = getenv("ASQ_DEBUG_TIMELINE");
+    p.dbg = (e != nullptr) ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
   const int cg = pick_cta_group(p.M);
   const int bn = (p.N > 128) ? 256 : (p.N > 64 ? 128 : 64);
   const int tile_m = asq::BLOCK_M * cg;
   p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
   p.num_n_blocks = (p.N + bn - 1) / bn;
   p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
-  {  // keep one group's W tiles (group_n * bn * K bytes) within ~48 MB of the 126 MB L2
+  {
+    // ASQ_RASTER=n | m<G> overrides the walk (experiments)
+    static int raster_env = -1, group_env = 0;
+    if (raster_env < 0) {
+      const char* e = getenv("ASQ_RASTER");
+      raster_env = 0;
+      if (e != nullptr && e[0] == 'm') { raster_env = 1; group_env = atoi(e + 1); }
+      else if (e != nullptr && e[0] == 'n') { raster_env = 2; group_env = atoi(e + 1); }
+    }
+    // default: keep one group's W tiles (group * bn * K bytes) within ~48 MB of the 126 MB L2
     const long long per_block = static_cast<long long>(bn) * p.K;
     long long gn = (48ll << 20) / per_block;
-    p.group_n = static_cast<int>(gn < 1 ? 1 : (gn > p.num_n_blocks ? p.num_n_blocks : gn));
+    p.raster_m = 0;
+    p.group = static_cast<int>(gn < 1 ? 1 : (gn > p.num_n_blocks ? p.num_n_blocks : gn));
+    if (raster_env == 1) { p.raster_m = 1; p.group = group_env > 0 ? group_env : p.num_m_blocks; }
+    if (raster_env == 2 && group_env > 0) p.group = group_env;
   }
   const long long tiles = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
   const int max_workers = st->sm_count / cg;
@@ -783,8 +911,24 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   if (rc != ASQ_OK) return rc;
   rc = make_tmap(&tmB, w, p.N, p.K, bn / cg);
   if (rc != ASQ_OK) return rc;
+  // Output map: y viewed as bytes [M, N*elem]; 32-row x 128-byte boxes (one epilogue warp's staging tile).
+  CUtensorMap tmY;
+  memset(&tmY, 0, sizeof(tmY));
+  {
+    const int elem = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16) ? 2 : (p.y_dtype == ASQ_I8 ? 1 : 4);
+    const long long row_bytes = static_cast<long long>(p.N) * elem;
+    static int no_tma_store = -1;
+    if (no_tma_store < 0) { const char* e = getenv("ASQ_NO_TMA_STORE"); no_tma_store = (e != nullptr && e[0] == '1'); }
+    p.tma_store = (!no_tma_store && elem != 1 && row_bytes % 16 == 0) ? 1 : 0;
+    if (p.tma_store) {
+      rc = make_tmap(&tmY, p.y, p.M, row_bytes, 32);
+      if (rc != ASQ_OK) return rc;
+    } else {
+      tmY = tmA;  // unused, but must be a valid descriptor
+    }
+  }
 
-#define ASQ_DISPATCH(F8, BNV, CGV) return launch_cfg<F8, BNV, CGV>(tmA, tmB, p, workers, stream)
+#define ASQ_DISPATCH(F8, BNV, CGV) return launch_cfg<F8, BNV, CGV>(tmA, tmB, tmY, p, workers, stream)
   if (fp8) {
     if (cg == 2) { if (bn == 256) ASQ_DISPATCH(true, 256, 2); if (bn == 128) ASQ_DISPATCH(true, 128, 2); ASQ_DISPATCH(true, 64, 2); }
     if (bn == 256) ASQ_DISPATCH(true, 256, 1); if (bn == 128) ASQ_DISPATCH(true, 128, 1); ASQ_DISPATCH(true, 64, 1);
