@@ -25,6 +25,7 @@ from .layers.nn.linear import (
     FP8LinearDynamic,
     W8A8BFP32OFP32Linear,
     W8A8BFP32OFP32LinearWithQuantScale,
+    W8A8BFP32OFP32QKVLinear,
 )
 
 
@@ -100,6 +101,24 @@ def _make_proj(kind: str, in_f: int, out_f: int, qcfg: Dict[str, str], input_sca
     return mod.to(device) if qcfg["type"] != "fp8_e4m3" else mod._apply(lambda t: t.to(device))
 
 
+def _fuse_columns(mods, device) -> W8A8BFP32OFP32QKVLinear:
+    """Horizontal fusion of projections that share their input (q/k/v, gate/up) into ONE launch with the
+    reference's fused-W_pack module (linear.py:132-245): weights concatenated along N, every block keeps its
+    own dequant scale, so the result is bit-identical to running the projections separately while the
+    activation is quantised once instead of once per projection."""
+    assert 2 <= len(mods) <= 3 and all(isinstance(m, W8A8BFP32OFP32Linear) for m in mods)
+    sizes = [m.out_features for m in mods] + [0] * (3 - len(mods))
+    first = mods[0]
+    fused = W8A8BFP32OFP32QKVLinear(sizes, first.in_features, sum(sizes), first.use_bias, first.act_quant)
+    fused.weight = torch.cat([m.weight for m in mods], dim=0).contiguous()
+    scales = [m.dequant_scale for m in mods] + [torch.tensor(1.0)] * (3 - len(mods))
+    for name, sc in zip(fused._scale_names, scales):
+        setattr(fused, name, sc.detach().clone().to(torch.float32).cpu())
+    if first.use_bias:
+        fused.bias = torch.cat([m.bias for m in mods]).contiguous()
+    return fused.to(device)
+
+
 def _rope_tables(seq: int, head_dim: int, theta: float, device, dtype):
     inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device, dtype=torch.float32) / head_dim))
     ang = torch.outer(torch.arange(seq, device=device, dtype=torch.float32), inv)
@@ -114,9 +133,10 @@ def _apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.
 
 
 class QuantDecoderLayer(nn.Module):
-    def __init__(self, cfg: DecoderConfig, qcfg: Dict[str, str], gen, device, dtype):
+    def __init__(self, cfg: DecoderConfig, qcfg: Dict[str, str], gen, device, dtype, fuse_projections: bool = False):
         super().__init__()
         self.cfg = cfg
+        self.fused = False
         h, kv, inter = cfg.hidden, cfg.kv_heads * cfg.head_dim, cfg.intermediate
         s = SYNTH_INPUT_SCALES
         self.q_proj = _make_proj("qkv", h, h, qcfg, s["attn_input"], gen, device)
@@ -136,8 +156,16 @@ class QuantDecoderLayer(nn.Module):
             ln2 = ln2 / s["gate_input"]
         self.register_buffer("input_layernorm_weight", ln1.to(dtype))
         self.register_buffer("post_attention_layernorm_weight", ln2.to(dtype))
+        if fuse_projections and int8:
+            self.qkv_sizes = [self.q_proj.out_features, self.k_proj.out_features, self.v_proj.out_features]
+            self.qkv_proj = _fuse_columns([self.q_proj, self.k_proj, self.v_proj], device)
+            self.gate_up_proj = _fuse_columns([self.gate_proj, self.up_proj], device)
+            del self.q_proj, self.k_proj, self.v_proj, self.gate_proj, self.up_proj
+            self.fused = True
 
     def linears(self):
+        if self.fused:
+            return [self.qkv_proj, self.o_proj, self.gate_up_proj, self.down_proj]
         return [self.q_proj, self.k_proj, self.v_proj, self.o_proj, self.gate_proj, self.up_proj, self.down_proj]
 
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
@@ -145,14 +173,22 @@ class QuantDecoderLayer(nn.Module):
         B, S, H = x.shape
         h = F.rms_norm(x, (H,), self.input_layernorm_weight, cfg.rms_eps)
         # head counts are inferred from the projection width so tensor-parallel shards (heads / p) work too
-        q = self.q_proj(h).view(B, S, -1, cfg.head_dim).transpose(1, 2)
-        k = self.k_proj(h).view(B, S, -1, cfg.head_dim).transpose(1, 2)
-        v = self.v_proj(h).view(B, S, -1, cfg.head_dim).transpose(1, 2)
+        if self.fused:
+            q, k, v = self.qkv_proj(h).split(self.qkv_sizes, dim=-1)
+        else:
+            q, k, v = self.q_proj(h), self.k_proj(h), self.v_proj(h)
+        q = q.view(B, S, -1, cfg.head_dim).transpose(1, 2)
+        k = k.view(B, S, -1, cfg.head_dim).transpose(1, 2)
+        v = v.view(B, S, -1, cfg.head_dim).transpose(1, 2)
         q, k = _apply_rope(q, cos, sin), _apply_rope(k, cos, sin)
         attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=k.shape[1] != q.shape[1])
         x = x + self.o_proj(attn.transpose(1, 2).reshape(B, S, -1))
         h = F.rms_norm(x, (H,), self.post_attention_layernorm_weight, cfg.rms_eps)
-        x = x + self.down_proj(F.silu(self.gate_proj(h)) * self.up_proj(h))
+        if self.fused:
+            gate, up = self.gate_up_proj(h).chunk(2, dim=-1)
+        else:
+            gate, up = self.gate_proj(h), self.up_proj(h)
+        x = x + self.down_proj(F.silu(gate) * up)
         return x
 
 
@@ -160,7 +196,7 @@ class QuantDecoder(nn.Module):
     """Embedding -> N quantized decoder layers -> norm -> lm_head (bf16, not quantized, as in the reference)."""
 
     def __init__(self, cfg: DecoderConfig, quant_config: Optional[Dict[str, str]] = None, device="cuda",
-                 dtype=torch.bfloat16, seed: int = 0, layers: Optional[int] = None):
+                 dtype=torch.bfloat16, seed: int = 0, layers: Optional[int] = None, fuse_projections: bool = False):
         super().__init__()
         self.cfg = cfg
         self.qcfg = normalise_quant_config(quant_config or {})
@@ -170,7 +206,8 @@ class QuantDecoder(nn.Module):
         self.embed = nn.Embedding(cfg.vocab, cfg.hidden, device=device, dtype=dtype)
         with torch.no_grad():
             self.embed.weight.normal_(0.0, 1.0, generator=gen)
-        self.layers = nn.ModuleList(QuantDecoderLayer(cfg, self.qcfg, gen, device, dtype) for _ in range(n_layers))
+        self.layers = nn.ModuleList(QuantDecoderLayer(cfg, self.qcfg, gen, device, dtype, fuse_projections)
+                                    for _ in range(n_layers))
         self.register_buffer("norm_weight", torch.ones(cfg.hidden, dtype=dtype, device=device))
         self.lm_head = nn.Linear(cfg.hidden, cfg.vocab, bias=False, device=device, dtype=dtype)
         with torch.no_grad():

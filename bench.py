@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--parallel", default="dp", choices=["dp", "tp"])
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="one launch per projection (q,k,v,gate,up separately) instead of the fused-W_pack module")
     return ap.parse_args()
 
 
@@ -197,7 +199,8 @@ def run_ours(args, cfg, layers):
         model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank)
         batch = args.batch * world  # weak scaling: the global batch grows with the GPU count
     else:
-        model = QuantDecoder(cfg, device=dev, dtype=torch.bfloat16, seed=0, layers=layers)
+        model = QuantDecoder(cfg, device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
+                             fuse_projections=not args.no_fuse)
         batch = args.batch
     B, S = batch, args.seq
     gen = torch.Generator().manual_seed(1234 + (rank if args.parallel == "dp" else 0))
@@ -217,6 +220,15 @@ def run_ours(args, cfg, layers):
     launches_before = _lib.launch_count()
     logits = model(ids_dev)
     launches_per_step = _lib.launch_count() - launches_before
+    if os.environ.get("ASQ_PROFILE_STEP"):
+        # profiling aid (ncu --profile-from-start off): expose exactly one eager step, then stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        model(ids_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_step": True, "launches_per_step": launches_per_step}))
+        return
     graph = None
     use_graph = not args.no_graph and not (args.parallel == "tp" and world > 1)
     if use_graph:
@@ -342,6 +354,8 @@ def run_ours(args, cfg, layers):
                             f"batch {args.batch} x seq {S} per GPU, bf16 activations",
                 "layers": layers, "global_batch": B * replicas, "seq_len": S,
                 "parallelism": f"{args.parallel}{world}", "cuda_graph": graph is not None,
+                "projections": "q|k|v and gate|up fused per layer via W8A8BFP32OFP32QKVLinear (4 launches/layer)"
+                               if not args.no_fuse else "one launch per projection (7 launches/layer)",
                 "l2": "weights (6.6 GB int8) and activations stream through the 126 MB L2 every step: inputs larger than L2",
                 "wall_s_timed_region": t_wall,
             },

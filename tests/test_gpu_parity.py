@@ -302,3 +302,41 @@ def test_full_size_properties(M, N, K):
     L.i8gemm_o32(q2, w, acc)
     y2 = L.w8a8_linear(x, w, None, L.ACT_SCALE, qs, ds)
     assert torch.equal(y2, (ds * acc).to(torch.bfloat16))
+
+
+# ----------------------------------------------------------------------------- model-level plumbing
+def test_fused_projections_equal_separate_projections():
+    """The benchmark stack fuses q|k|v and gate|up through W8A8BFP32OFP32QKVLinear; per-block dequant scales
+    make that bit-identical to one launch per projection."""
+    from autosmoothquant_b200 import harness
+
+    ids = torch.randint(0, harness.TINY.vocab, (2, 64), generator=torch.Generator().manual_seed(0)).to(DEV)
+    for qc in ({}, {"qkv": "per-token", "out": "per-token", "fc1": "per-token", "fc2": "per-token"}):
+        a = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=3, fuse_projections=False)
+        b = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=3, fuse_projections=True)
+        ya, yb = a(ids, last_token_only=False), b(ids, last_token_only=False)
+        assert torch.isfinite(ya).all()
+        assert torch.equal(ya, yb)
+
+
+def test_decoder_layer_matches_oracle_linears(exact_div):
+    """One decoder layer's quantized projections, module by module, against the oracle on the activations the
+    layer actually produces (per-tensor config: round-only qkv/fc1, quant-scale out/fc2)."""
+    from autosmoothquant_b200 import harness
+
+    model = harness.QuantDecoder(harness.TINY, {}, device=DEV, seed=5)
+    layer = model.layers[0]
+    captured = {}
+    hooks = [m.register_forward_hook(lambda mod, inp, out, name=n: captured.__setitem__(name, (inp[0], out)))
+             for n, m in layer.named_children()]
+    ids = torch.randint(0, harness.TINY.vocab, (1, 48), generator=torch.Generator().manual_seed(1)).to(DEV)
+    model(ids)
+    for h in hooks:
+        h.remove()
+    assert set(captured) == {"q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"}
+    for name, (x, y) in captured.items():
+        mod = getattr(layer, name)
+        want = O.w8a8_linear(x.float().cpu().numpy(), "bf16", mod.weight.cpu().numpy(), float(mod.dequant_scale),
+                             act_quant="per-tensor",
+                             quant_scale=float(mod.quant_scale) if hasattr(mod, "quant_scale") else None)
+        np.testing.assert_array_equal(y.float().cpu().numpy(), want, err_msg=name)
