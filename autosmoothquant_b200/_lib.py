@@ -43,6 +43,10 @@ EXPORTED_SYMBOLS = (
     "asq_i8gemm_o32",
     "asq_i8gemm_epi",
     "asq_quantize_act",
+    "asq_w8a8_linear_q8",
+    "asq_add_rmsnorm_quant",
+    "asq_silu_mul_quant",
+    "asq_rope_inplace",
 )
 
 _lib = None
@@ -107,6 +111,14 @@ def load():
         lib.asq_i8gemm_epi.argtypes = [c_vp, c_vp, c_vp, c_i, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_f, c_i, c_vp]
         lib.asq_quantize_act.restype = c_i
         lib.asq_quantize_act.argtypes = [c_vp, c_i, c_vp, c_vp, c_i64, c_i64, c_i, c_f, c_i, c_i, c_vp]
+        lib.asq_w8a8_linear_q8.restype = c_i
+        lib.asq_w8a8_linear_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp, c_vp]
+        lib.asq_add_rmsnorm_quant.restype = c_i
+        lib.asq_add_rmsnorm_quant.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_f, c_vp]
+        lib.asq_silu_mul_quant.restype = c_i
+        lib.asq_silu_mul_quant.argtypes = [c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_i, c_vp, c_vp, c_vp]
+        lib.asq_rope_inplace.restype = c_i
+        lib.asq_rope_inplace.argtypes = [c_vp, c_i, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]
         _lib = lib
     return _lib
 
@@ -354,3 +366,102 @@ def quantize_act(
     if fp8:
         q = q.view(torch.float8_e4m3fn)
     return q, rs
+
+
+# ---------------------------------------------------------------- producer-side fusions (asq_glue.cu)
+def w8a8_linear_q8(
+    xq: torch.Tensor,
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    dequant_scale: float = 1.0,
+    col_scale: Optional[torch.Tensor] = None,
+    row_scale: Optional[torch.Tensor] = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+) -> torch.Tensor:
+    """INT8 GEMM + dequant epilogue for activations a fused producer already quantised (no prologue)."""
+    global _launches
+    dev = _require_cuda(xq, weight, bias, col_scale, row_scale)
+    if xq.dtype != torch.int8 or weight.dtype != torch.int8 or xq.dim() != 2 or xq.shape[1] != weight.shape[1]:
+        raise ValueError("w8a8_linear_q8 expects int8 [M,K] activations and int8 [N,K] weights")
+    if not (xq.is_contiguous() and weight.is_contiguous()):
+        raise ValueError("w8a8_linear_q8 expects contiguous tensors")
+    M, K = xq.shape
+    N = weight.shape[0]
+    y = torch.empty((M, N), dtype=out_dtype, device=dev)
+    if M == 0:
+        return y
+    with torch.cuda.device(dev):
+        rc = load().asq_w8a8_linear_q8(xq.data_ptr(), _ptr(row_scale), weight.data_ptr(), _ptr(bias), y.data_ptr(),
+                                       _code(out_dtype), M, N, K, float(dequant_scale), _ptr(col_scale), _stream(dev))
+    _check(rc)
+    _launches += 1
+    return y
+
+
+def add_rmsnorm_quant(
+    x: torch.Tensor,
+    delta: Optional[torch.Tensor],
+    weight: torch.Tensor,
+    eps: float,
+    want_h: bool = False,
+    want_q: bool = True,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """(x + delta, rmsnorm(x + delta) * weight in x's dtype, its int8 rounding); x is [M,H], updated out of place."""
+    global _launches
+    dev = _require_cuda(x, delta, weight)
+    if x.dim() != 2 or not x.is_contiguous() or (delta is not None and (delta.shape != x.shape or not delta.is_contiguous())):
+        raise ValueError("add_rmsnorm_quant expects contiguous [M,H] tensors")
+    M, H = x.shape
+    x_out = torch.empty_like(x) if delta is not None else x
+    h = torch.empty_like(x) if want_h else None
+    q = torch.empty((M, H), dtype=torch.int8, device=dev) if want_q else None
+    if M > 0:
+        with torch.cuda.device(dev):
+            rc = load().asq_add_rmsnorm_quant(x.data_ptr(), _ptr(delta), weight.data_ptr(),
+                                              x_out.data_ptr() if delta is not None else None, _ptr(h), _ptr(q),
+                                              _code(x.dtype), M, H, float(eps), _stream(dev))
+        _check(rc)
+        _launches += 1
+    return x_out, h, q
+
+
+def silu_mul_quant(
+    gate_up: torch.Tensor,
+    quant_scale: float = 1.0,
+    want_q: bool = True,
+    want_a: bool = False,
+    div_mode: Optional[int] = None,
+) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """gate_up [M, 2I] -> (int8 sat(rint(T(a / quant_scale))), a = T(T(silu(gate)) * up)), each optional."""
+    global _launches
+    dev = _require_cuda(gate_up)
+    if gate_up.dim() != 2 or gate_up.shape[1] % 2 or gate_up.stride(1) != 1:
+        raise ValueError("silu_mul_quant expects a [M, 2I] tensor with unit inner stride")
+    M, I = gate_up.shape[0], gate_up.shape[1] // 2
+    q = torch.empty((M, I), dtype=torch.int8, device=dev) if want_q else None
+    a = torch.empty((M, I), dtype=gate_up.dtype, device=dev) if want_a else None
+    if M > 0:
+        with torch.cuda.device(dev):
+            rc = load().asq_silu_mul_quant(gate_up.data_ptr(), _code(gate_up.dtype), M, I, gate_up.stride(0),
+                                           float(quant_scale), _default_div_mode if div_mode is None else div_mode,
+                                           _ptr(q), _ptr(a), _stream(dev))
+        _check(rc)
+        _launches += 1
+    return q, a
+
+
+def rope_inplace(qk: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int, n_heads: int, head_dim: int) -> None:
+    """Rotate-half RoPE in place on the first n_heads*head_dim columns of qk [M, row]; position = row % seq_len."""
+    global _launches
+    dev = _require_cuda(qk, cos, sin)
+    if qk.dim() != 2 or qk.stride(1) != 1 or cos.dtype != qk.dtype or sin.dtype != qk.dtype:
+        raise ValueError("rope_inplace expects [M, row] activations and tables of the same dtype")
+    if tuple(cos.shape) != (seq_len, head_dim) or tuple(sin.shape) != (seq_len, head_dim) or not (cos.is_contiguous() and sin.is_contiguous()):
+        raise ValueError("cos/sin tables must be contiguous [seq_len, head_dim]")
+    if qk.shape[0] == 0:
+        return
+    with torch.cuda.device(dev):
+        rc = load().asq_rope_inplace(qk.data_ptr(), _code(qk.dtype), cos.data_ptr(), sin.data_ptr(), qk.shape[0], seq_len,
+                                     qk.stride(0), n_heads, head_dim, _stream(dev))
+    _check(rc)
+    _launches += 1

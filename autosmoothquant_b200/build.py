@@ -14,7 +14,7 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-SOURCES = [PKG_DIR / "csrc" / "asq_kernels.cu"]
+SOURCES = [PKG_DIR / "csrc" / "asq_kernels.cu", PKG_DIR / "csrc" / "asq_glue.cu"]
 HEADERS = [PKG_DIR / "csrc" / "asq_ptx.cuh", REPO_ROOT / "include" / "asq.h"]
 LIB_PATH = PKG_DIR / "libasq_b200.so"
 

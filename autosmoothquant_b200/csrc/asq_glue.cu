@@ -1,0 +1,288 @@
+// asq_glue.cu — producer-side fusions around the W8A8 linear.
+//
+// The reference folds 1/input_scale into the norm weight (models/llama.py:27-37, 326-339) so the
+// per-tensor Linear only rounds and saturates its input (linear.py:95); its dead `LayerNormQ` /
+// `dq_add_layernorm_q` (layers/nn/fused.py:2-25, csrc/kernels/fused.cu:5-24) show the intent: let the
+// producer of an activation emit the int8 tensor the GEMM consumes.  These kernels do that for the
+// Llama block, so three of the four GEMM launches of a layer need no phase 1 at all:
+//
+//   asq_add_rmsnorm_quant   x (+= delta) ; h = w * T(x * rsqrt(mean(x^2)+eps)) ; q = sat(rint(h))   -> qkv / gate|up
+//   asq_silu_mul_quant      a = T(T(silu(g)) * u) ; q = sat(rint(T(a / quant_scale)))                -> down_proj
+//   asq_rope_inplace        HF rotate-half RoPE applied in place to the q and k blocks of the fused qkv output
+//
+// All are HBM-bound elementwise / row-reduction kernels: 16-byte vector accesses, one warp per row
+// (row reductions by warp shuffles), grid sized to the SM count.  Every intermediate is rounded to the
+// activation dtype T exactly where eager torch would round it, so the int8 they emit equals what the
+// module path (norm -> Linear.forward) would have produced up to the summation order of the variance.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/asq.h"
+
+int asq_glue_fail(int code, const char* fmt, ...);  // defined in asq_kernels.cu (shares the error buffer)
+
+namespace asq_glue {
+
+template <typename T>
+struct Cvt;
+template <>
+struct Cvt<__nv_bfloat16> {
+  __device__ static __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+  __device__ static __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+  __device__ static __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <>
+struct Cvt<__half> {
+  __device__ static __forceinline__ float lo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu))); }
+  __device__ static __forceinline__ float hi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
+  __device__ static __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = Cvt<T>::lo(v.x); f[1] = Cvt<T>::hi(v.x); f[2] = Cvt<T>::lo(v.y); f[3] = Cvt<T>::hi(v.y);
+  f[4] = Cvt<T>::lo(v.z); f[5] = Cvt<T>::hi(v.z); f[6] = Cvt<T>::lo(v.w); f[7] = Cvt<T>::hi(v.w);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(Cvt<T>::pack(f[0], f[1]), Cvt<T>::pack(f[2], f[3]), Cvt<T>::pack(f[4], f[5]), Cvt<T>::pack(f[6], f[7]));
+}
+__device__ __forceinline__ uint32_t s8x4(float v0, float v1, float v2, float v3) {
+  int i0, i1, i2, i3;
+  asm("cvt.rni.sat.s32.f32 %0, %1;" : "=r"(i0) : "f"(v0));
+  asm("cvt.rni.sat.s32.f32 %0, %1;" : "=r"(i1) : "f"(v1));
+  asm("cvt.rni.sat.s32.f32 %0, %1;" : "=r"(i2) : "f"(v2));
+  asm("cvt.rni.sat.s32.f32 %0, %1;" : "=r"(i3) : "f"(v3));
+  uint32_t hi, out;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(i3), "r"(i2), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(i1), "r"(i0), "r"(hi));
+  return out;
+}
+
+// ------------------------------------------------------------------ add + RMSNorm (+ int8)
+// One warp per row; the row (H <= 8192 16-bit elements) is held in registers between the two passes.
+constexpr int NORM_MAXV = 32;  // 16-byte vectors per lane: H <= 32 * 32 * 8 = 8192
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(const T* __restrict__ x, const T* __restrict__ delta,
+                                                                const T* __restrict__ weight, T* __restrict__ x_out,
+                                                                T* __restrict__ h_out, int8_t* __restrict__ q_out,
+                                                                int M, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int nvec = H / 8;  // vectors per row
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
+    const uint4* dr = delta ? reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H) : nullptr;
+    uint4 buf[NV];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int v = lane + j * 32;
+      if (v < nvec) {
+        uint4 a = __ldg(xr + v);
+        if (dr != nullptr) {
+          float fa[8], fd[8];
+          unpack8<T>(a, fa);
+          unpack8<T>(__ldg(dr + v), fd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) fa[i] = __fadd_rn(fa[i], fd[i]);  // x + delta, rounded to T by pack8
+          a = pack8<T>(fa);
+          if (x_out != nullptr) reinterpret_cast<uint4*>(x_out + static_cast<size_t>(row) * H)[v] = a;
+        }
+        buf[j] = a;
+        float f[8];
+        unpack8<T>(a, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int v = lane + j * 32;
+      if (v < nvec) {
+        float f[8], w[8];
+        unpack8<T>(buf[j], f);
+        unpack8<T>(__ldg(reinterpret_cast<const uint4*>(weight) + v), w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = Cvt<T>::rnd(__fmul_rn(w[i], Cvt<T>::rnd(__fmul_rn(f[i], rstd))));  // w * T(x*rstd)
+        if (h_out != nullptr) reinterpret_cast<uint4*>(h_out + static_cast<size_t>(row) * H)[v] = pack8<T>(f);
+        if (q_out != nullptr)
+          reinterpret_cast<uint2*>(q_out + static_cast<size_t>(row) * H)[v] =
+              make_uint2(s8x4(f[0], f[1], f[2], f[3]), s8x4(f[4], f[5], f[6], f[7]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ SiLU(gate) * up (+ int8)
+// gate_up rows are [gate(I) | up(I)] with `row_stride` elements between rows (the fused gate|up GEMM output).
+template <typename T>
+__global__ void __launch_bounds__(256) silu_mul_quant_kernel(const T* __restrict__ gate_up, long long row_stride, int M, int I,
+                                                             float quant_scale, float inv_quant_scale, int div_mode,
+                                                             int8_t* __restrict__ q_out, T* __restrict__ a_out) {
+  const int vec_per_row = I / 8;
+  const long long total = static_cast<long long>(M) * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(idx / vec_per_row);
+    const int v = static_cast<int>(idx - static_cast<long long>(row) * vec_per_row);
+    const T* base = gate_up + static_cast<size_t>(row) * row_stride;
+    float g[8], u[8];
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(base) + v), g);
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(base + I) + v), u);
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s = Cvt<T>::rnd(__fdiv_rn(g[i], 1.0f + expf(-g[i])));  // T(silu(g)), fp32 math like torch
+      a[i] = Cvt<T>::rnd(__fmul_rn(s, u[i]));
+    }
+    if (a_out != nullptr) reinterpret_cast<uint4*>(a_out + static_cast<size_t>(row) * I)[v] = pack8<T>(a);
+    if (q_out != nullptr) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        t[i] = Cvt<T>::rnd(div_mode == ASQ_DIV_RECIPROCAL ? __fmul_rn(a[i], inv_quant_scale) : __fdiv_rn(a[i], quant_scale));
+      reinterpret_cast<uint2*>(q_out + static_cast<size_t>(row) * I)[v] =
+          make_uint2(s8x4(t[0], t[1], t[2], t[3]), s8x4(t[4], t[5], t[6], t[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ RoPE in place (HF rotate-half)
+// qk: rows of `row_stride` elements; the first n_heads * head_dim elements of each row are rotated.
+// out[d] = T(T(x[d]*cos[d]) + T(rot[d]*sin[d])), rot[d] = d < hd/2 ? -x[d+hd/2] : x[d-hd/2]; cos/sin: [S, hd] of T.
+template <typename T>
+__global__ void __launch_bounds__(256) rope_kernel(T* __restrict__ qk, long long row_stride, const T* __restrict__ cos_t,
+                                                   const T* __restrict__ sin_t, int M, int S, int n_heads, int head_dim) {
+  const int half_vecs = head_dim / 16;  // 16-byte vectors in half a head
+  const long long total = static_cast<long long>(M) * n_heads * half_vecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % half_vecs);
+    const long long hh = idx / half_vecs;
+    const int head = static_cast<int>(hh % n_heads);
+    const int row = static_cast<int>(hh / n_heads);
+    const int pos = row % S;
+    T* p = qk + static_cast<size_t>(row) * row_stride + static_cast<size_t>(head) * head_dim;
+    uint4* lo_p = reinterpret_cast<uint4*>(p) + v;
+    uint4* hi_p = reinterpret_cast<uint4*>(p + head_dim / 2) + v;
+    const uint4* c_lo = reinterpret_cast<const uint4*>(cos_t + static_cast<size_t>(pos) * head_dim) + v;
+    const uint4* s_lo = reinterpret_cast<const uint4*>(sin_t + static_cast<size_t>(pos) * head_dim) + v;
+    const uint4* c_hi = reinterpret_cast<const uint4*>(cos_t + static_cast<size_t>(pos) * head_dim + head_dim / 2) + v;
+    const uint4* s_hi = reinterpret_cast<const uint4*>(sin_t + static_cast<size_t>(pos) * head_dim + head_dim / 2) + v;
+    float xl[8], xh[8], cl[8], sl[8], ch[8], sh[8], ol[8], oh[8];
+    unpack8<T>(*lo_p, xl);
+    unpack8<T>(*hi_p, xh);
+    unpack8<T>(__ldg(c_lo), cl);
+    unpack8<T>(__ldg(s_lo), sl);
+    unpack8<T>(__ldg(c_hi), ch);
+    unpack8<T>(__ldg(s_hi), sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ol[i] = __fadd_rn(Cvt<T>::rnd(__fmul_rn(xl[i], cl[i])), Cvt<T>::rnd(__fmul_rn(-xh[i], sl[i])));
+      oh[i] = __fadd_rn(Cvt<T>::rnd(__fmul_rn(xh[i], ch[i])), Cvt<T>::rnd(__fmul_rn(xl[i], sh[i])));
+    }
+    *lo_p = pack8<T>(ol);
+    *hi_p = pack8<T>(oh);
+  }
+}
+
+int grid_for(long long work_items, int per_block) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(sms) * 8;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace asq_glue
+
+extern "C" {
+
+int asq_add_rmsnorm_quant(const void* x, const void* delta, const void* weight, void* x_out, void* h_out,
+                          int8_t* q_out, int dtype, int64_t M, int64_t H, float eps, void* stream) {
+  using namespace asq_glue;
+  if (dtype != ASQ_BF16 && dtype != ASQ_F16) return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: dtype must be f16 or bf16");
+  if (M < 0 || H <= 0 || H % 8 != 0 || H > 32 * 8 * NORM_MAXV)
+    return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: H=%lld must be a multiple of 8 and <= %d", (long long)H, 32 * 8 * NORM_MAXV);
+  if (M == 0) return ASQ_OK;
+  if (x == nullptr || weight == nullptr || (h_out == nullptr && q_out == nullptr) || (delta != nullptr && x_out == nullptr))
+    return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: null pointer argument");
+  if (!aligned16(x) || !aligned16(weight) || !aligned16(delta) || !aligned16(x_out) || !aligned16(h_out) || !aligned16(q_out))
+    return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: pointers must be 16-byte aligned");
+  const int grid = grid_for(M, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ASQ_NORM_LAUNCH(TT, NVV)                                                                                   \
+  add_rmsnorm_quant_kernel<TT, NVV><<<grid, 256, 0, st>>>(static_cast<const TT*>(x), static_cast<const TT*>(delta),   \
+                                                          static_cast<const TT*>(weight), static_cast<TT*>(x_out),   \
+                                                          static_cast<TT*>(h_out), q_out, (int)M, (int)H, eps)
+  const bool small = H <= 32 * 8 * 16;
+  if (dtype == ASQ_BF16) { if (small) ASQ_NORM_LAUNCH(__nv_bfloat16, 16); else ASQ_NORM_LAUNCH(__nv_bfloat16, 32); }
+  else                   { if (small) ASQ_NORM_LAUNCH(__half, 16); else ASQ_NORM_LAUNCH(__half, 32); }
+#undef ASQ_NORM_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ASQ_OK : asq_glue_fail(ASQ_ERR_CUDA, "rmsnorm launch failed: %s", cudaGetErrorString(e));
+}
+
+int asq_silu_mul_quant(const void* gate_up, int dtype, int64_t M, int64_t I, int64_t row_stride, float quant_scale,
+                       int div_mode, int8_t* q_out, void* a_out, void* stream) {
+  using namespace asq_glue;
+  if (dtype != ASQ_BF16 && dtype != ASQ_F16) return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: dtype must be f16 or bf16");
+  if (M < 0 || I <= 0 || I % 8 != 0 || row_stride < 2 * I || row_stride % 8 != 0)
+    return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: bad shape M=%lld I=%lld stride=%lld", (long long)M, (long long)I, (long long)row_stride);
+  if (M == 0) return ASQ_OK;
+  if (gate_up == nullptr || (q_out == nullptr && a_out == nullptr)) return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: null pointer argument");
+  if (!aligned16(gate_up) || !aligned16(q_out) || !aligned16(a_out)) return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: pointers must be 16-byte aligned");
+  const int grid = grid_for(M * (I / 8), 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == ASQ_BF16)
+    silu_mul_quant_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(gate_up), row_stride, (int)M, (int)I,
+                                                               quant_scale, 1.0f / quant_scale, div_mode, q_out,
+                                                               static_cast<__nv_bfloat16*>(a_out));
+  else
+    silu_mul_quant_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(gate_up), row_stride, (int)M, (int)I, quant_scale,
+                                                        1.0f / quant_scale, div_mode, q_out, static_cast<__half*>(a_out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ASQ_OK : asq_glue_fail(ASQ_ERR_CUDA, "silu_mul launch failed: %s", cudaGetErrorString(e));
+}
+
+int asq_rope_inplace(void* qk, int dtype, const void* cos_table, const void* sin_table, int64_t M, int64_t S,
+                     int64_t row_stride, int64_t n_heads, int64_t head_dim, void* stream) {
+  using namespace asq_glue;
+  if (dtype != ASQ_BF16 && dtype != ASQ_F16) return asq_glue_fail(ASQ_ERR_INVALID, "rope: dtype must be f16 or bf16");
+  if (M < 0 || S <= 0 || n_heads <= 0 || head_dim <= 0 || head_dim % 16 != 0 || row_stride < n_heads * head_dim || row_stride % 8 != 0)
+    return asq_glue_fail(ASQ_ERR_INVALID, "rope: bad shape");
+  if (M == 0) return ASQ_OK;
+  if (qk == nullptr || cos_table == nullptr || sin_table == nullptr) return asq_glue_fail(ASQ_ERR_INVALID, "rope: null pointer argument");
+  if (!aligned16(qk) || !aligned16(cos_table) || !aligned16(sin_table)) return asq_glue_fail(ASQ_ERR_INVALID, "rope: pointers must be 16-byte aligned");
+  const int grid = grid_for(M * n_heads * (head_dim / 16), 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == ASQ_BF16)
+    rope_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(qk), row_stride, static_cast<const __nv_bfloat16*>(cos_table),
+                                                     static_cast<const __nv_bfloat16*>(sin_table), (int)M, (int)S, (int)n_heads, (int)head_dim);
+  else
+    rope_kernel<__half><<<grid, 256, 0, st>>>(static_cast<__half*>(qk), row_stride, static_cast<const __half*>(cos_table),
+                                              static_cast<const __half*>(sin_table), (int)M, (int)S, (int)n_heads, (int)head_dim);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ASQ_OK : asq_glue_fail(ASQ_ERR_CUDA, "rope launch failed: %s", cudaGetErrorString(e));
+}
+
+}  // extern "C"

@@ -784,6 +784,19 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+// error reporting shared with asq_glue.cu
+int asq_glue_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+namespace {
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1063,6 +1076,23 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
   const float ds = (act_mode == ASQ_ACT_PER_TOKEN || act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? w_scale : w_scale * in_scale;
   return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, in_scale, ds, nullptr,
                       row_scale_out, div_mode, workspace, workspace_bytes, stream);
+}
+
+int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,
+                       int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                       void* stream) {
+  int rc = check_common(xq, w, y, M, N, K);
+  if (rc != ASQ_OK || M == 0) return rc;
+  if (!is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "y dtype must be f32, f16 or bf16");
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT;
+  // phase 1 is skipped (p.x == nullptr); the epilogue reads caller-supplied per-token scales if given
+  p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
+  p.row_scale = const_cast<float*>(row_scale);
+  return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream));
 }
 
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c, int64_t M, int64_t N, int64_t K, void* stream) {

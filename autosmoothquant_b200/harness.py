@@ -119,6 +119,14 @@ def _fuse_columns(mods, device) -> W8A8BFP32OFP32QKVLinear:
     return fused.to(device)
 
 
+def rms_norm_hf(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    """HF LlamaRMSNorm.forward (what the reference's QuantizedLlamaRMSNorm inherits, models/llama.py:27-37):
+    normalise in fp32, round to the activation dtype, then multiply by the (folded) weight."""
+    xf = x.float()
+    n = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype)
+    return weight * n
+
+
 def _rope_tables(seq: int, head_dim: int, theta: float, device, dtype):
     inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device, dtype=torch.float32) / head_dim))
     ang = torch.outer(torch.arange(seq, device=device, dtype=torch.float32), inv)
@@ -171,7 +179,7 @@ class QuantDecoderLayer(nn.Module):
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
         cfg = self.cfg
         B, S, H = x.shape
-        h = F.rms_norm(x, (H,), self.input_layernorm_weight, cfg.rms_eps)
+        h = rms_norm_hf(x, self.input_layernorm_weight, cfg.rms_eps)
         # head counts are inferred from the projection width so tensor-parallel shards (heads / p) work too
         if self.fused:
             q, k, v = self.qkv_proj(h).split(self.qkv_sizes, dim=-1)
@@ -183,7 +191,7 @@ class QuantDecoderLayer(nn.Module):
         q, k = _apply_rope(q, cos, sin), _apply_rope(k, cos, sin)
         attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=k.shape[1] != q.shape[1])
         x = x + self.o_proj(attn.transpose(1, 2).reshape(B, S, -1))
-        h = F.rms_norm(x, (H,), self.post_attention_layernorm_weight, cfg.rms_eps)
+        h = rms_norm_hf(x, self.post_attention_layernorm_weight, cfg.rms_eps)
         if self.fused:
             gate, up = self.gate_up_proj(h).chunk(2, dim=-1)
         else:
@@ -192,14 +200,51 @@ class QuantDecoderLayer(nn.Module):
         return x
 
 
+def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Optional[torch.Tensor], B: int, S: int,
+                        cos: torch.Tensor, sin: torch.Tensor):
+    """One decoder layer with the producer-side fusions of asq_glue.cu (per-tensor INT8, fused projections):
+    add+RMSNorm emits the int8 input of qkv / gate|up, SiLU*up emits the int8 input of down_proj, RoPE runs
+    in place on the fused qkv output; only o_proj (fed by the attention library kernel) still quantises
+    inside its own launch.  x2: residual stream [M,H]; delta: the previous block's output not yet added."""
+    from . import _lib
+
+    cfg = layer.cfg
+    hd = cfg.head_dim
+    x2, _, q8 = _lib.add_rmsnorm_quant(x2, delta, layer.input_layernorm_weight, cfg.rms_eps)
+    qkv_mod = layer.qkv_proj
+    qkv = _lib.w8a8_linear_q8(q8, qkv_mod.weight, qkv_mod.bias if qkv_mod.use_bias else None, 1.0,
+                              col_scale=qkv_mod._col_scale(x2.device), out_dtype=x2.dtype)
+    nq, nk, nv = (n // hd for n in layer.qkv_sizes)
+    _lib.rope_inplace(qkv, cos, sin, S, nq + nk, hd)
+    q, k, v = qkv.split(layer.qkv_sizes, dim=-1)
+    q = q.view(B, S, nq, hd).transpose(1, 2)
+    k = k.view(B, S, nk, hd).transpose(1, 2)
+    v = v.view(B, S, nv, hd).transpose(1, 2)
+    attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=nk != nq)
+    o = layer.o_proj(attn.transpose(1, 2).reshape(B * S, nq * hd))
+    x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
+    gu_mod = layer.gate_up_proj
+    gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
+                             col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
+    down = layer.down_proj
+    a8, _ = _lib.silu_mul_quant(gu, float(down.quant_scale.item()))
+    d = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
+                            out_dtype=x2.dtype)
+    return x2, d
+
+
 class QuantDecoder(nn.Module):
     """Embedding -> N quantized decoder layers -> norm -> lm_head (bf16, not quantized, as in the reference)."""
 
     def __init__(self, cfg: DecoderConfig, quant_config: Optional[Dict[str, str]] = None, device="cuda",
-                 dtype=torch.bfloat16, seed: int = 0, layers: Optional[int] = None, fuse_projections: bool = False):
+                 dtype=torch.bfloat16, seed: int = 0, layers: Optional[int] = None, fuse_projections: bool = False,
+                 glue: bool = False):
         super().__init__()
         self.cfg = cfg
         self.qcfg = normalise_quant_config(quant_config or {})
+        # producer-side fusions need the fused projections and the all-per-tensor INT8 configuration
+        self.glue = bool(glue and fuse_projections and self.qcfg["type"] == "int8"
+                         and all(self.qcfg[k] == "per-tensor" for k in ("qkv", "out", "fc1", "fc2")))
         self.dtype = dtype
         gen = torch.Generator(device=device).manual_seed(seed)
         n_layers = cfg.layers if layers is None else layers
@@ -225,11 +270,22 @@ class QuantDecoder(nn.Module):
             self._rope = (S, cos, sin)
         _, cos, sin = self._rope
         x = self.embed(input_ids)
+        if self.glue:
+            from . import _lib
+
+            x2, delta = x.view(B * S, -1), None
+            for layer in self.layers:
+                x2, delta = _layer_forward_glue(layer, x2, delta, B, S, cos, sin)
+            if last_token_only:  # only the last position of every sequence feeds the lm_head
+                x2 = x2.view(B, S, -1)[:, -1, :].contiguous()
+                delta = delta.view(B, S, -1)[:, -1, :].contiguous()
+            _, h, _ = _lib.add_rmsnorm_quant(x2, delta, self.norm_weight, self.cfg.rms_eps, want_h=True, want_q=False)
+            return self.lm_head(h.view(B, -1, self.cfg.hidden)).float()
         for layer in self.layers:
             x = layer(x, cos, sin)
         if last_token_only:
             x = x[:, -1:, :]
-        x = F.rms_norm(x, (self.cfg.hidden,), self.norm_weight, self.cfg.rms_eps)
+        x = rms_norm_hf(x, self.norm_weight, self.cfg.rms_eps)
         return self.lm_head(x).float()
 
 

@@ -132,6 +132,13 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
                    float* row_scale_out, int div_mode,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same GEMM + dequant epilogue for activations that are ALREADY int8 (emitted by a fused producer such as
+ * asq_add_rmsnorm_quant / asq_silu_mul_quant): no prologue runs.  row_scale [M] fp32 or NULL supplies
+ * per-token scales for the epilogue. */
+int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
+                       void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                       float dequant_scale, const float* col_scale, void* stream);
+
 /* c[M,N] (int32) = a[M,K] (int8) . w[N,K]^T (int8), exact.  Drop-in for
  * I8CUGEMM::linear_a8_w8_o32_ and the exactness tap of the fused kernels. */
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c,
@@ -150,6 +157,26 @@ int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_
 int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale,
                      int64_t M, int64_t K, int act_mode, float quant_scale,
                      int div_mode, int fp8, void* stream);
+
+/* ---- producer-side fusions (reference intent: layers/nn/fused.py:2-25,
+ * csrc/kernels/fused.cu:5-24, norm folding models/llama.py:27-37,326-339).  dtype in {F16, BF16}. ---- */
+
+/* x_out = T(x + delta) (when delta != NULL); h = T(weight * T(x_out * rsqrt(mean(x_out^2) + eps)));
+ * h_out (T, nullable) receives h, q_out (int8, nullable) receives sat(rint(h)) — the int8 tensor the
+ * per-tensor W8A8BFP32OFP32Linear would derive from h (linear.py:95).  H % 8 == 0, H <= 8192. */
+int asq_add_rmsnorm_quant(const void* x, const void* delta, const void* weight, void* x_out, void* h_out,
+                          int8_t* q_out, int dtype, int64_t M, int64_t H, float eps, void* stream);
+
+/* gate_up rows = [gate (I) | up (I)], row_stride elements apart.  a = T(T(silu(gate)) * up);
+ * a_out (T, nullable) receives a, q_out (int8, nullable) receives sat(rint(T(a / quant_scale))) — what
+ * W8A8BFP32OFP32LinearWithQuantScale derives from a (linear.py:290-292). */
+int asq_silu_mul_quant(const void* gate_up, int dtype, int64_t M, int64_t I, int64_t row_stride,
+                       float quant_scale, int div_mode, int8_t* q_out, void* a_out, void* stream);
+
+/* HF rotate-half RoPE in place on the first n_heads*head_dim elements of each of M rows (row_stride
+ * elements apart); position = row % S; cos/sin tables [S, head_dim] of T. */
+int asq_rope_inplace(void* qk, int dtype, const void* cos_table, const void* sin_table, int64_t M, int64_t S,
+                     int64_t row_stride, int64_t n_heads, int64_t head_dim, void* stream);
 
 #ifdef __cplusplus
 }

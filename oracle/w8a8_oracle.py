@@ -331,3 +331,35 @@ def tp_row_parallel_int32(q: np.ndarray, weight: np.ndarray, world: int) -> np.n
     parts = [int8_gemm_i32(np.ascontiguousarray(q[:, r * kp:(r + 1) * kp]),
                            np.ascontiguousarray(weight[:, r * kp:(r + 1) * kp])) for r in range(world)]
     return np.sum(np.stack(parts).astype(np.int64), axis=0).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------- producer-side fusions (asq_glue.cu)
+def add_rmsnorm_quant(x: np.ndarray, delta: Optional[np.ndarray], weight: np.ndarray, eps: float, dtype: str):
+    """Residual add + HF LlamaRMSNorm.forward (inherited by the reference's QuantizedLlamaRMSNorm,
+    models/llama.py:27-37, weight already divided by the input scale) + the rounding the per-tensor Linear
+    applies to its input (linear.py:95).  Returns (x + delta in T, h in T, int8 sat(rint(h)))."""
+    x = np.asarray(x, F32)
+    if delta is not None:
+        x = round_to(x + np.asarray(delta, F32), dtype)
+    var = np.mean(x.astype(np.float64) ** 2, axis=-1, keepdims=True).astype(F32)
+    n = round_to(x * (F32(1.0) / np.sqrt(var + F32(eps))).astype(F32), dtype)
+    h = round_to(np.asarray(weight, F32) * n, dtype)
+    return x, h, sat_i8(np.rint(h))
+
+
+def silu_mul_quant(gate: np.ndarray, up: np.ndarray, quant_scale: float, dtype: str, div_mode: str = "exact"):
+    """a = T(T(silu(gate)) * up) (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x)) and the int8 tensor
+    W8A8BFP32OFP32LinearWithQuantScale derives from it (linear.py:290-292)."""
+    g = np.asarray(gate, F32)
+    s = round_to((g.astype(np.float64) / (1.0 + np.exp(-g.astype(np.float64)))).astype(F32), dtype)
+    a = round_to(s * np.asarray(up, F32), dtype)
+    q = sat_i8(np.rint(_scalar_div(a, quant_scale, dtype, div_mode)))
+    return a, q
+
+
+def rope_rotate_half(x: np.ndarray, cos: np.ndarray, sin: np.ndarray, dtype: str) -> np.ndarray:
+    """HF apply_rotary_pos_emb for one tensor: T(T(x*cos) + T(rotate_half(x)*sin)); x [..., S, hd]."""
+    x = np.asarray(x, F32)
+    half = x.shape[-1] // 2
+    rot = np.concatenate([-x[..., half:], x[..., :half]], axis=-1)
+    return round_to(round_to(x * cos, dtype) + round_to(rot * sin, dtype), dtype)

@@ -340,3 +340,100 @@ def test_decoder_layer_matches_oracle_linears(exact_div):
                              act_quant="per-tensor",
                              quant_scale=float(mod.quant_scale) if hasattr(mod, "quant_scale") else None)
         np.testing.assert_array_equal(y.float().cpu().numpy(), want, err_msg=name)
+
+
+# ----------------------------------------------------------------------------- producer-side fusions (asq_glue.cu)
+def _frac_bad(got, want):
+    return float(np.mean(got != want))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("H", [256, 4096, 5120, 8192])
+def test_add_rmsnorm_quant(dtype, H):
+    """fp32 row reduction: the summation order differs from the oracle's fp64 mean, so a last-place flip of
+    rstd may move a handful of outputs by one ulp / one int8 step; everything else must be identical."""
+    rng = np.random.default_rng(H)
+    M = 67
+    x = O.round_to(rng.standard_normal((M, H)).astype(np.float32) * 2, dtype)
+    d = O.round_to(rng.standard_normal((M, H)).astype(np.float32), dtype)
+    w = O.round_to((1.0 + 0.1 * rng.standard_normal(H)).astype(np.float32) / 0.035, dtype)  # folded 1/input_scale
+    for delta in (None, d):
+        xs, h, q = L.add_rmsnorm_quant(t(x, TORCH_DT[dtype]), None if delta is None else t(delta, TORCH_DT[dtype]),
+                                       t(w, TORCH_DT[dtype]), 1e-5, want_h=True, want_q=True)
+        xw, hw, qw = O.add_rmsnorm_quant(x, delta, w, 1e-5, dtype)
+        np.testing.assert_array_equal(xs.float().cpu().numpy(), xw)
+        hg = h.float().cpu().numpy()
+        assert _frac_bad(hg, hw) < 5e-3
+        np.testing.assert_allclose(hg, hw, rtol=2 ** -6 if dtype == "bf16" else 2 ** -9, atol=0)  # <= 2 ulp (two roundings)
+        qg = q.cpu().numpy().astype(np.int32)
+        assert np.abs(qg - qw.astype(np.int32)).max() <= 1 and _frac_bad(qg, qw) < 5e-3
+        # the int8 output is exactly the rounding of the kernel's own h (what Linear.forward would compute)
+        np.testing.assert_array_equal(qg, O.sat_i8(np.rint(hg)))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_silu_mul_quant(dtype, exact_div):
+    rng = np.random.default_rng(3)
+    M, I = 45, 1376
+    gu = O.round_to(rng.standard_normal((M, 2 * I)).astype(np.float32) * 2, dtype)
+    q, a = L.silu_mul_quant(t(gu, TORCH_DT[dtype]), 0.0631, want_q=True, want_a=True)
+    aw, qw = O.silu_mul_quant(gu[:, :I], gu[:, I:], 0.0631, dtype)
+    ag = a.float().cpu().numpy()
+    assert _frac_bad(ag, aw) < 2e-3  # expf vs fp64 exp: rare one-ulp differences before rounding to T
+    np.testing.assert_allclose(ag, aw, rtol=2 ** -6 if dtype == "bf16" else 2 ** -9, atol=1e-30)
+    qg = q.cpu().numpy().astype(np.int32)
+    assert np.abs(qg - qw.astype(np.int32)).max() <= 1 and _frac_bad(qg, qw) < 2e-3
+    # int8 output == the module path applied to the kernel's own activation
+    np.testing.assert_array_equal(qg, O.quantize_act_int8(ag, dtype, "scale", 0.0631)[0])
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_rope_inplace_bit_exact(dtype):
+    rng = np.random.default_rng(9)
+    B, S, nq, nk, hd = 2, 37, 6, 2, 64
+    row = (nq + 2 * nk) * hd
+    qkv = O.round_to(rng.standard_normal((B * S, row)).astype(np.float32), dtype)
+    ang = np.outer(np.arange(S), 1.0 / (10000.0 ** (np.arange(0, hd, 2) / hd))).astype(np.float32)
+    emb = np.concatenate([ang, ang], axis=-1)
+    cos, sin = O.round_to(np.cos(emb), dtype), O.round_to(np.sin(emb), dtype)
+    buf = t(qkv, TORCH_DT[dtype])
+    L.rope_inplace(buf, t(cos, TORCH_DT[dtype]), t(sin, TORCH_DT[dtype]), S, nq + nk, hd)
+    got = buf.float().cpu().numpy()
+    want = qkv.copy()
+    heads = qkv[:, :(nq + nk) * hd].reshape(B, S, nq + nk, hd).transpose(0, 2, 1, 3)  # [B, heads, S, hd]
+    rot = O.rope_rotate_half(heads, cos, sin, dtype).transpose(0, 2, 1, 3).reshape(B * S, -1)
+    want[:, :(nq + nk) * hd] = rot
+    np.testing.assert_array_equal(got, want)  # v block untouched, q/k rotated exactly
+
+
+def test_linear_q8_equals_module_path(exact_div):
+    """Pre-quantised entry point == fused entry point when fed the same int8 activations."""
+    rng = np.random.default_rng(6)
+    M, N, K = 300, 520, 1040
+    x = make_x(rng, M, K, "bf16", 40.0)
+    w = rng.integers(-127, 128, size=(N, K), dtype=np.int8)
+    b = rng.standard_normal(N).astype(np.float32)
+    y1 = L.w8a8_linear(t(x, torch.bfloat16), t(w), t(b), L.ACT_ROUND, 1.0, 0.004)
+    q, _ = L.quantize_act(t(x, torch.bfloat16), L.ACT_ROUND)
+    y2 = L.w8a8_linear_q8(q, t(w), t(b), 0.004)
+    assert torch.equal(y1, y2)
+    y3 = L.w8a8_linear(t(x, torch.bfloat16), t(w), t(b), L.ACT_PER_TOKEN, 1.0, 0.004)
+    q, s = L.quantize_act(t(x, torch.bfloat16), L.ACT_PER_TOKEN)
+    y4 = L.w8a8_linear_q8(q, t(w), t(b), 0.004, row_scale=s)
+    assert torch.equal(y3, y4)
+
+
+def test_glue_stack_close_to_module_stack():
+    """Whole tiny decoder: producer-fused path vs module path.  Not bit-identical by construction (the fp32
+    variance is summed in a different order), so compare logits with a tolerance."""
+    from autosmoothquant_b200 import harness
+
+    ids = torch.randint(0, harness.TINY.vocab, (2, 64), generator=torch.Generator().manual_seed(0)).to(DEV)
+    a = harness.QuantDecoder(harness.TINY, {}, device=DEV, seed=3, fuse_projections=True, glue=False)
+    b = harness.QuantDecoder(harness.TINY, {}, device=DEV, seed=3, fuse_projections=True, glue=True)
+    assert b.glue
+    for last in (False, True):
+        ya, yb = a(ids, last_token_only=last), b(ids, last_token_only=last)
+        assert ya.shape == yb.shape and torch.isfinite(yb).all()
+        assert float((ya - yb).abs().max()) <= 0.05 * float(ya.abs().max())
+        assert float((ya != yb).float().mean()) < 0.5
