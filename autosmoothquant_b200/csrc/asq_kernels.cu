@@ -72,7 +72,8 @@ struct LinearParams {
   float dequant_scale, alpha, beta;
   int M, N, K;
   int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
-  int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;
+  int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;  // num_n_blocks = TILE_N-wide tiles per row
+  int n_units, rounds, tail_tiles, tail_q;                        // balanced schedule (see TileWalk)
   int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
   unsigned long long* dbg;  // optional timeline buffer (8 slots per CTA), nullptr in production
 };
@@ -461,24 +462,29 @@ __device__ __forceinline__ void tile_coords(int t, const LinearParams& p, int& m
   }
 }
 
-// BN = accumulator width (UMMA N).  CG = CTAs per tile: 1 -> a 128 x BN tile per CTA; 2 -> a CTA pair
-// (cta_group::2) owns a 256 x BN tile: each CTA stages its own 128 A rows and HALF of the W tile, the
-// leader issues 256 x BN MMAs that read both CTAs' shared memory, each CTA drains its own 128 TMEM lanes.
-// Pairing halves the W bytes every SM pulls from L2 per MMA, which is what bounds 8-bit GEMMs here.
+// Tile geometry.  CG = CTAs per tile: 1 -> a 128-row tile per CTA; 2 -> a CTA pair (cta_group::2) owns a
+// 256-row tile: each CTA stages its own 128 A rows and HALF of the W tile, the leader issues 256 x N MMAs
+// that read both CTAs' shared memory, each CTA drains its own 128 TMEM lanes.  Pairing cuts the bytes
+// every SM pulls from L2 per MMA by a third, which is what bounds 8-bit GEMMs at full clock.
+// Tiles are up to TILE_N = 256 columns wide; the scheduler may hand out narrower tiles in units of
+// UNIT_N = 64 columns (UMMA N = 64/128/192/256) to balance the last, partial round of tiles.
+constexpr int TILE_N = 256;
+constexpr int UNIT_N = 64;
 constexpr uint32_t EPI_BUF_BYTES = 32 * 128;  // one warp's staging tile: 32 rows x 128 bytes
 constexpr uint32_t EPI_NBUF = 2;              // double-buffered per warp
 constexpr uint32_t EPI_BYTES = NUM_EPI_WARPS * EPI_BUF_BYTES * EPI_NBUF;
 constexpr uint32_t SMEM_LIMIT = 232448;       // 227 KB per CTA on sm_100
 
-template <int BN, int CG>
+template <int CG>
 struct TileCfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K;
-  static constexpr uint32_t B_ROWS = BN / CG;  // W rows staged per CTA
+  static constexpr uint32_t B_ROWS = TILE_N / CG;  // W rows staged per CTA for a full-width tile
+  static constexpr uint32_t UNIT_ROWS = UNIT_N / CG;
   static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t BUDGET = SMEM_LIMIT - EPI_BYTES - 256 - 1024;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr uint32_t TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
   static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;  // multiple of 1024
   static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr uint32_t SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
@@ -486,12 +492,51 @@ struct TileCfg {
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
+// The sequence of tiles one worker (CTA or CTA pair) processes; every warp role walks it identically.
+//   rounds x  full tiles  t = round * W + worker            (round-robin, TILE_N wide)
+//   then      the R = T - rounds * W left-over tiles are cut into 64-column units and dealt `tail_q` units
+//             per worker, so the last round costs tail_q/4 of a tile instead of a whole one.
+struct TileWalk {
+  const LinearParams& p;
+  int worker, W, round, g, g_end;
+  __device__ TileWalk(const LinearParams& p_, int worker_, int W_) : p(p_), worker(worker_), W(W_), round(0) {
+    g = worker_ * p_.tail_q;
+    g_end = min(g + p_.tail_q, p_.tail_tiles * (TILE_N / UNIT_N));
+  }
+  __device__ bool next(int& m_blk, int& col0, int& width) {
+    constexpr int U = TILE_N / UNIT_N;
+    int n_blk;
+    if (round < p.rounds) {
+      tile_coords(round * W + worker, p, m_blk, n_blk);
+      ++round;
+      col0 = n_blk * TILE_N;
+      width = min(U, p.n_units - n_blk * U) * UNIT_N;
+      return true;
+    }
+    while (g < g_end) {
+      const int j = g / U, k = g % U;
+      tile_coords(p.rounds * W + j, p, m_blk, n_blk);
+      const int nu = n_blk * U + k;
+      const int avail = min(U - k, g_end - g);
+      g += avail;
+      const int wu = min(avail, p.n_units - nu);
+      if (wu > 0) {
+        col0 = nu * UNIT_N;
+        width = wu * UNIT_N;
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
 // ------------------------------------------------------------------ the kernel
-template <bool FP8, int BN, int CG>
+template <bool FP8, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmY, const LinearParams p) {
-  using Cfg = TileCfg<BN, CG>;
+                  const __grid_constant__ CUtensorMap tmBu, const __grid_constant__ CUtensorMap tmY,
+                  const LinearParams p) {
+  using Cfg = TileCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -512,13 +557,14 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int num_workers = gridDim.x / CG;                        // CTAs (CG=1) or CTA pairs (CG=2)
   const int worker = blockIdx.x / CG;
-  const int total_tiles = p.num_m_blocks * p.num_n_blocks;       // num_m_blocks counts TILE_M-row tiles
   const bool fused = (p.x != nullptr);
   if (threadIdx.x == 0) ASQ_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmBu);
+    tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx; TMA bytes of both CTAs land here
       mbar_init(empty_bar(s), 1);  // one tcgen05.commit (multicast to both CTAs of a pair)
@@ -544,47 +590,63 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = worker; t < total_tiles; t += num_workers) {
-        int m_blk, n_blk;
-        tile_coords(t, p, m_blk, n_blk);
+      bool first = true;
+      TileWalk walk(p, worker, num_workers);
+      int m_blk, col0, width;
+      while (walk.next(m_blk, col0, width)) {
         const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's A rows
+        const int b_rows = width / CG;                                                  // this CTA's W rows
+        const int w_row = col0 + static_cast<int>(cta_rank) * b_rows;
+        const uint32_t stage_tx = CG * (Cfg::A_BYTES + static_cast<uint32_t>(b_rows) * BLOCK_K);
         bool panel_ready = !fused || row0 >= p.M;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+          if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), stage_tx);
           const uint32_t sA = base + stage * Cfg::A_BYTES;
           const uint32_t sB = base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES;
-          const int w_row = n_blk * BN + static_cast<int>(cta_rank) * static_cast<int>(Cfg::B_ROWS);
           // W does not depend on phase 1: issue it before (possibly) waiting for the A panel
-          if (CG == 2) tma_load_2d_pair(sB, &tmB, full_bar(stage), kb * BLOCK_K, w_row);
-          else         tma_load_2d(sB, &tmB, full_bar(stage), kb * BLOCK_K, w_row);
+          if (width == TILE_N) {
+            if (CG == 2) tma_load_2d_pair(sB, &tmB, full_bar(stage), kb * BLOCK_K, w_row);
+            else         tma_load_2d(sB, &tmB, full_bar(stage), kb * BLOCK_K, w_row);
+          } else {
+            for (int u = 0; u * UNIT_N < width; ++u) {  // narrow tile: one 64-column unit per load
+              const uint32_t dst = sB + u * (Cfg::UNIT_ROWS * BLOCK_K);
+              const int r = w_row + u * static_cast<int>(Cfg::UNIT_ROWS);
+              if (CG == 2) tma_load_2d_pair(dst, &tmBu, full_bar(stage), kb * BLOCK_K, r);
+              else         tma_load_2d(dst, &tmBu, full_bar(stage), kb * BLOCK_K, r);
+            }
+          }
           if (!panel_ready) {
             const uint32_t need = static_cast<uint32_t>(min(BLOCK_M, p.M - row0));
             const uint32_t* flag = p.sync + 1 + row0 / BLOCK_M;
             while (ld_acquire_gpu(flag) < need) __nanosleep(64);
             fence_proxy_async_all();  // phase-1 generic-proxy stores -> TMA (async proxy) reads
             panel_ready = true;
-            if (t == worker) ASQ_STAMP(3);
+            if (first) ASQ_STAMP(3);
           }
           if (CG == 2) tma_load_2d_pair(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
           else         tma_load_2d(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc(FP8, BLOCK_M * CG, BN);
+      constexpr uint32_t idesc_base = make_idesc(FP8, BLOCK_M * CG, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = worker; t < total_tiles; t += num_workers, ++it) {
+      TileWalk walk(p, worker, num_workers);
+      int m_blk, col0, width;
+      for (; walk.next(m_blk, col0, width); ++it) {
+        const uint32_t idesc = idesc_base | (static_cast<uint32_t>(width >> 3) << 17);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogues (both CTAs) drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * TILE_N;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -630,46 +692,48 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (ew == 0 && lane == 0) ASQ_STAMP(2);
     }
     // ===================== phase 2: epilogue =====================
-    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;           // which half of the BN columns
-    constexpr int CHUNKS = BN / 2 / 32; // 32-column chunks per warp
+    // A tile is width/64 column groups; warps with half == 0 take the even groups, half == 1 the odd ones.
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty_leader1 = (CG == 2) ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
     const uint32_t stage_base = base + Cfg::EPI_OFFSET + ew * (EPI_BUF_BYTES * EPI_NBUF);
     const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
-    const bool staged = p.tma_store && (!out16 || CHUNKS >= 2);
+    const bool staged = p.tma_store != 0;
     const int elem = out16 ? 2 : 4;
+    const bool per_token_epi = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) &&
+                               p.epi_kind == EPI_DEQUANT;
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     int it = 0;
-    for (int t = worker; t < total_tiles; t += num_workers, ++it) {
-      int m_blk, n_blk;
-      tile_coords(t, p, m_blk, n_blk);
+    TileWalk walk(p, worker, num_workers);
+    int m_blk, tile_col0, width;
+    for (; walk.next(m_blk, tile_col0, width); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quad * 32;
       const int row = row0 + lane;
-      const int col_base = n_blk * BN + half * (BN / 2);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
+      const int ngroups = width / UNIT_N;
       float rs = 0.f;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (it == 0 && ew == 0 && lane == 0) ASQ_STAMP(5);
-      if ((p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) && p.epi_kind == EPI_DEQUANT && row < p.M)
-        rs = __ldcg(p.row_scale + row);
-      if (staged && out16) {
-        // 64 output columns (two TMEM chunks) fill one 128-byte wide staging tile
+      if (per_token_epi && row < p.M) rs = __ldcg(p.row_scale + row);
 #pragma unroll 1
-        for (int g = 0; g < CHUNKS / 2; ++g) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(taddr + g * 64, r0);
-          tmem_ld_32x32(taddr + g * 64 + 32, r1);
+      for (int g = half; g < ngroups; g += 2) {
+        const uint32_t taddr = taddr0 + g * UNIT_N;
+        const int col0 = tile_col0 + g * UNIT_N;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(taddr, r0);
+        tmem_ld_32x32(taddr + 32, r1);
+        if (staged && out16) {
+          // 64 output columns (two TMEM chunks) fill one 128-byte wide staging tile
           const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
           if (gcount >= EPI_NBUF) {  // the store that last used this buffer must have read it
             if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
             __syncwarp();
           }
           tmem_ld_wait();
-          const int col0 = col_base + g * 64;
           float v[32];
           uint32_t w[16];
           epilogue_values<FP8>(r0, v, col0, rs, p);
@@ -685,46 +749,40 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_store_commit();
           }
           ++gcount;
-        }
-      } else if (staged) {
-        // 4-byte outputs: one TMEM chunk (32 columns) is one 128-byte wide staging tile
-#pragma unroll 1
-        for (int ch = 0; ch < CHUNKS; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
-          const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
-          if (gcount >= EPI_NBUF) {
-            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
-            __syncwarp();
-          }
+        } else if (staged) {
+          // 4-byte outputs: each TMEM chunk (32 columns) is one 128-byte wide staging tile
           tmem_ld_wait();
-          const int col0 = col_base + ch * 32;
-          if (p.epi_kind == EPI_RAW_I32) {
-            stage_words<32>(buf, lane, 0, r);
-          } else {
-            float v[32];
-            uint32_t w[32];
-            epilogue_values<FP8>(r, v, col0, rs, p);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              w[j] = (p.y_dtype == ASQ_I32) ? static_cast<uint32_t>(__float2int_rn(v[j])) : __float_as_uint(v[j]);
-            stage_words<32>(buf, lane, 0, w);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+            if (gcount >= EPI_NBUF) {
+              if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
+              __syncwarp();
+            }
+            const int c0 = col0 + h * 32;
+            if (p.epi_kind == EPI_RAW_I32) {
+              stage_words<32>(buf, lane, 0, h ? r1 : r0);
+            } else {
+              float v[32];
+              uint32_t w[32];
+              epilogue_values<FP8>(h ? r1 : r0, v, c0, rs, p);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                w[j] = (p.y_dtype == ASQ_I32) ? static_cast<uint32_t>(__float2int_rn(v[j])) : __float_as_uint(v[j]);
+              stage_words<32>(buf, lane, 0, w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && c0 < p.N) {
+              tma_store_2d(&tmY, buf, c0 * elem, row0);
+              tma_store_commit();
+            }
+            ++gcount;
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && row0 < p.M && col0 < p.N) {
-            tma_store_2d(&tmY, buf, col0 * elem, row0);
-            tma_store_commit();
-          }
-          ++gcount;
-        }
-      } else {
-#pragma unroll 1
-        for (int ch = 0; ch < CHUNKS; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
+        } else {
           tmem_ld_wait();
-          store_chunk_direct<FP8>(r, row, col_base + ch * 32, rs, p);
+          store_chunk_direct<FP8>(r0, row, col0, rs, p);
+          store_chunk_direct<FP8>(r1, row, col0 + 32, rs, p);
         }
       }
       tc_fence_before();
@@ -879,11 +937,11 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
   return kSyncBytes + rs + aq;
 }
 
-template <bool FP8, int BN, int CG>
-int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const asq::LinearParams& p,
-               int workers, cudaStream_t stream) {
-  using Cfg = asq::TileCfg<BN, CG>;
-  auto kern = asq::asq_linear_kernel<FP8, BN, CG>;
+template <bool FP8, int CG>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBu, const CUtensorMap& tmY,
+               const asq::LinearParams& p, int workers, cudaStream_t stream) {
+  using Cfg = asq::TileCfg<CG>;
+  auto kern = asq::asq_linear_kernel<FP8, CG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   cudaLaunchConfig_t cfg;
@@ -899,13 +957,13 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, p);
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBu, tmY, p);
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
 }
 
-// Tile shape selection.  CTA pairs (256-row tiles) whenever there are at least two 128-row panels; the
-// accumulator width follows N.  ASQ_FORCE_CG=1|2 overrides the pairing (profiling / tests).
+// CTA pairs (256-row tiles) whenever there is more than one 128-row panel.  ASQ_FORCE_CG=1|2 overrides
+// the pairing (profiling / tests).
 int pick_cta_group(int64_t M) {
   static int forced = -1;
   if (forced < 0) {
@@ -924,19 +982,19 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   if (rc != ASQ_OK) return rc;
   if (!st->supported)
     return fail(ASQ_ERR_CUDA, "device %d is not compute capability 10.0 (sm_100a kernels only)", dev);
-
   {  // ASQ_DEBUG_TIMELINE=<device pointer, hex>: per-CTA phase timestamps (profiling builds of the caller)
     const char* e = getenv("ASQ_DEBUG_TIMELINE");
     p.dbg = (e != nullptr) ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 16)) : nullptr;
   }
   const int cg = pick_cta_group(p.M);
-  const int bn = (p.N > 128) ? 256 : (p.N > 64 ? 128 : 64);
   const int tile_m = asq::BLOCK_M * cg;
+  constexpr int U = asq::TILE_N / asq::UNIT_N;
   p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
-  p.num_n_blocks = (p.N + bn - 1) / bn;
+  p.n_units = (p.N + asq::UNIT_N - 1) / asq::UNIT_N;
+  p.num_n_blocks = (p.n_units + U - 1) / U;
   p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
   {
-    // ASQ_RASTER=n | m<G> overrides the walk (experiments)
+    // ASQ_RASTER=n<G> | m<G> overrides the walk (experiments)
     static int raster_env = -1, group_env = 0;
     if (raster_env < 0) {
       const char* e = getenv("ASQ_RASTER");
@@ -944,22 +1002,38 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (e != nullptr && e[0] == 'm') { raster_env = 1; group_env = atoi(e + 1); }
       else if (e != nullptr && e[0] == 'n') { raster_env = 2; group_env = atoi(e + 1); }
     }
-    // default: keep one group's W tiles (group * bn * K bytes) within ~48 MB of the 126 MB L2
-    const long long per_block = static_cast<long long>(bn) * p.K;
+    // default: keep one group's W tiles (group * 256 * K bytes) within ~48 MB of the 126 MB L2
+    const long long per_block = static_cast<long long>(asq::TILE_N) * p.K;
     long long gn = (48ll << 20) / per_block;
     p.raster_m = 0;
     p.group = static_cast<int>(gn < 1 ? 1 : (gn > p.num_n_blocks ? p.num_n_blocks : gn));
     if (raster_env == 1) { p.raster_m = 1; p.group = group_env > 0 ? group_env : p.num_m_blocks; }
     if (raster_env == 2 && group_env > 0) p.group = group_env;
   }
+  // Balanced schedule: `rounds` full tiles per worker, then the left-over tiles dealt in 64-column units.
   const long long tiles = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
   const int max_workers = st->sm_count / cg;
-  const int workers = static_cast<int>(tiles < max_workers ? tiles : max_workers);
+  // Measured on B200 (profiles/r01_notes.md): narrow tail tiles are L2-feed bound (a 256x64 pair tile moves
+  // 20 KB per 128 MMA cycles), so dealing the last round in 64-column units is slower than one more round
+  // of full tiles; the split stays available for experiments (ASQ_TAIL_SPLIT=1).
+  static int no_split = -1;
+  if (no_split < 0) { const char* e = getenv("ASQ_TAIL_SPLIT"); no_split = !(e != nullptr && e[0] == '1'); }
+  int workers = max_workers;
+  p.rounds = static_cast<int>(tiles / max_workers);
+  p.tail_tiles = static_cast<int>(tiles - static_cast<long long>(p.rounds) * max_workers);
+  if (p.tail_tiles > 0) {
+    p.tail_q = no_split ? U : (p.tail_tiles * U + max_workers - 1) / max_workers;
+    if (p.rounds == 0) workers = (p.tail_tiles * U + p.tail_q - 1) / p.tail_q;
+  } else {
+    p.tail_q = 0;
+  }
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBu;
   rc = make_tmap(&tmA, a8, p.M, p.K, asq::BLOCK_M);
   if (rc != ASQ_OK) return rc;
-  rc = make_tmap(&tmB, w, p.N, p.K, bn / cg);
+  rc = make_tmap(&tmB, w, p.N, p.K, asq::TILE_N / cg);
+  if (rc != ASQ_OK) return rc;
+  rc = make_tmap(&tmBu, w, p.N, p.K, asq::UNIT_N / cg);
   if (rc != ASQ_OK) return rc;
   // Output map: y viewed as bytes [M, N*elem]; 32-row x 128-byte boxes (one epilogue warp's staging tile).
   CUtensorMap tmY;
@@ -977,15 +1051,10 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       tmY = tmA;  // unused, but must be a valid descriptor
     }
   }
-
-#define ASQ_DISPATCH(F8, BNV, CGV) return launch_cfg<F8, BNV, CGV>(tmA, tmB, tmY, p, workers, stream)
-  if (fp8) {
-    if (cg == 2) { if (bn == 256) ASQ_DISPATCH(true, 256, 2); if (bn == 128) ASQ_DISPATCH(true, 128, 2); ASQ_DISPATCH(true, 64, 2); }
-    if (bn == 256) ASQ_DISPATCH(true, 256, 1); if (bn == 128) ASQ_DISPATCH(true, 128, 1); ASQ_DISPATCH(true, 64, 1);
-  }
-  if (cg == 2) { if (bn == 256) ASQ_DISPATCH(false, 256, 2); if (bn == 128) ASQ_DISPATCH(false, 128, 2); ASQ_DISPATCH(false, 64, 2); }
-  if (bn == 256) ASQ_DISPATCH(false, 256, 1); if (bn == 128) ASQ_DISPATCH(false, 128, 1); ASQ_DISPATCH(false, 64, 1);
-#undef ASQ_DISPATCH
+  if (fp8) return cg == 2 ? launch_cfg<true, 2>(tmA, tmB, tmBu, tmY, p, workers, stream)
+                          : launch_cfg<true, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
+  return cg == 2 ? launch_cfg<false, 2>(tmA, tmB, tmBu, tmY, p, workers, stream)
+                 : launch_cfg<false, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
 }
 
 int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {
