@@ -71,95 +71,135 @@ __device__ __forceinline__ uint32_t s8x4(float v0, float v1, float v2, float v3)
 }
 
 // ------------------------------------------------------------------ add + RMSNorm (+ int8)
-// One warp per row; the row (H <= 8192 16-bit elements) is held in registers between the two passes.
-constexpr int NORM_MAXV = 32;  // 16-byte vectors per lane: H <= 32 * 32 * 8 = 8192
+// One 128-thread CTA per row (grid = M: a single balanced wave, ~14 CTAs resident per SM); each thread
+// keeps its NV 16-byte vectors of the row in registers between the two passes; sum of squares by warp
+// shuffles + a 4-entry shared array.
+constexpr int NORM_THREADS = 128;
+constexpr int NORM_MAXV = 8;  // vectors per thread: H <= 128 * 8 * 8 = 8192
 
 template <typename T, int NV>
-__global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(const T* __restrict__ x, const T* __restrict__ delta,
-                                                                const T* __restrict__ weight, T* __restrict__ x_out,
-                                                                T* __restrict__ h_out, int8_t* __restrict__ q_out,
-                                                                int M, int H, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int warps = gridDim.x * (blockDim.x >> 5);
+__global__ void __launch_bounds__(NORM_THREADS) add_rmsnorm_quant_kernel(const T* x, const T* __restrict__ delta,
+                                                                         const T* __restrict__ weight, T* x_out,
+                                                                         T* __restrict__ h_out, int8_t* __restrict__ q_out,
+                                                                         int M, int H, float eps) {
+  __shared__ float warp_sums[NORM_THREADS / 32];
+  const int row = blockIdx.x;
   const int nvec = H / 8;  // vectors per row
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
-    const uint4* dr = delta ? reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H) : nullptr;
-    uint4 buf[NV];
-    float ss = 0.f;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
+  const uint4* dr = delta ? reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H) : nullptr;
+  uint4 buf[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = threadIdx.x + j * NORM_THREADS;
+    if (v < nvec) buf[j] = xr[v];
+  }
+  if (dr != nullptr) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int v = lane + j * 32;
+      const int v = threadIdx.x + j * NORM_THREADS;
       if (v < nvec) {
-        uint4 a = __ldg(xr + v);
-        if (dr != nullptr) {
-          float fa[8], fd[8];
-          unpack8<T>(a, fa);
-          unpack8<T>(__ldg(dr + v), fd);
+        float fa[8], fd[8];
+        unpack8<T>(buf[j], fa);
+        unpack8<T>(__ldg(dr + v), fd);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) fa[i] = __fadd_rn(fa[i], fd[i]);  // x + delta, rounded to T by pack8
-          a = pack8<T>(fa);
-          if (x_out != nullptr) reinterpret_cast<uint4*>(x_out + static_cast<size_t>(row) * H)[v] = a;
-        }
-        buf[j] = a;
-        float f[8];
-        unpack8<T>(a, f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+        for (int i = 0; i < 8; ++i) fa[i] = __fadd_rn(fa[i], fd[i]);  // x + delta, rounded to T by pack8
+        buf[j] = pack8<T>(fa);
+        reinterpret_cast<uint4*>(x_out + static_cast<size_t>(row) * H)[v] = buf[j];
       }
     }
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+  for (int j = 0; j < NV; ++j) {
+    const int v = threadIdx.x + j * NORM_THREADS;
+    if (v < nvec) {
+      float f[8];
+      unpack8<T>(buf[j], f);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = lane + j * 32;
-      if (v < nvec) {
-        float f[8], w[8];
-        unpack8<T>(buf[j], f);
-        unpack8<T>(__ldg(reinterpret_cast<const uint4*>(weight) + v), w);
+      for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+    }
+  }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = Cvt<T>::rnd(__fmul_rn(w[i], Cvt<T>::rnd(__fmul_rn(f[i], rstd))));  // w * T(x*rstd)
-        if (h_out != nullptr) reinterpret_cast<uint4*>(h_out + static_cast<size_t>(row) * H)[v] = pack8<T>(f);
-        if (q_out != nullptr)
-          reinterpret_cast<uint2*>(q_out + static_cast<size_t>(row) * H)[v] =
-              make_uint2(s8x4(f[0], f[1], f[2], f[3]), s8x4(f[4], f[5], f[6], f[7]));
-      }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  ss = warp_sums[0] + warp_sums[1] + warp_sums[2] + warp_sums[3];
+  const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = threadIdx.x + j * NORM_THREADS;
+    if (v < nvec) {
+      float f[8], w[8];
+      unpack8<T>(buf[j], f);
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(weight) + v), w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = Cvt<T>::rnd(__fmul_rn(w[i], Cvt<T>::rnd(__fmul_rn(f[i], rstd))));  // w * T(x*rstd)
+      if (h_out != nullptr) reinterpret_cast<uint4*>(h_out + static_cast<size_t>(row) * H)[v] = pack8<T>(f);
+      if (q_out != nullptr)
+        reinterpret_cast<uint2*>(q_out + static_cast<size_t>(row) * H)[v] =
+            make_uint2(s8x4(f[0], f[1], f[2], f[3]), s8x4(f[4], f[5], f[6], f[7]));
     }
   }
 }
 
 // ------------------------------------------------------------------ SiLU(gate) * up (+ int8)
 // gate_up rows are [gate(I) | up(I)] with `row_stride` elements between rows (the fused gate|up GEMM output).
+// silu uses the SFU approximations (ex2.approx / rcp.approx, relative error ~2^-21) and is then rounded to
+// the 8-bit-mantissa activation dtype, so it differs from an IEEE evaluation in about 1e-4 of the elements by
+// one ulp of T; with expf + IEEE division the kernel is ALU-bound at twice the runtime.
+template <typename T>
+__device__ __forceinline__ void silu_mul_vec(const uint4& gv, const uint4& uv, float quant_scale, float inv_quant_scale,
+                                             int div_mode, int8_t* q_dst, T* a_dst) {
+  float g[8], u[8], a[8];
+  unpack8<T>(gv, g);
+  unpack8<T>(uv, u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float s = Cvt<T>::rnd(__fdividef(g[i], 1.0f + __expf(-g[i])));  // T(silu(g))
+    a[i] = Cvt<T>::rnd(__fmul_rn(s, u[i]));
+  }
+  if (a_dst != nullptr) *reinterpret_cast<uint4*>(a_dst) = pack8<T>(a);
+  if (q_dst != nullptr) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      t[i] = Cvt<T>::rnd(div_mode == ASQ_DIV_RECIPROCAL ? __fmul_rn(a[i], inv_quant_scale) : __fdiv_rn(a[i], quant_scale));
+    *reinterpret_cast<uint2*>(q_dst) = make_uint2(s8x4(t[0], t[1], t[2], t[3]), s8x4(t[4], t[5], t[6], t[7]));
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) silu_mul_quant_kernel(const T* __restrict__ gate_up, long long row_stride, int M, int I,
                                                              float quant_scale, float inv_quant_scale, int div_mode,
                                                              int8_t* __restrict__ q_out, T* __restrict__ a_out) {
-  const int vec_per_row = I / 8;
-  const long long total = static_cast<long long>(M) * vec_per_row;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int row = static_cast<int>(idx / vec_per_row);
-    const int v = static_cast<int>(idx - static_cast<long long>(row) * vec_per_row);
+  // 32-bit index arithmetic (the host checks M * I / 8 < 2^31): 64-bit divisions would dominate the loop
+  const uint32_t vec_per_row = static_cast<uint32_t>(I) / 8u;
+  const uint32_t total = static_cast<uint32_t>(M) * vec_per_row;
+  const uint32_t step = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += 2 * step) {
+    // two independent vectors per iteration: four 16-byte loads in flight per thread
+    const uint32_t idx2 = idx + step;
+    const uint32_t row = idx / vec_per_row;
+    const uint32_t v = idx - row * vec_per_row;
     const T* base = gate_up + static_cast<size_t>(row) * row_stride;
-    float g[8], u[8];
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(base) + v), g);
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(base + I) + v), u);
-    float a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float s = Cvt<T>::rnd(__fdiv_rn(g[i], 1.0f + expf(-g[i])));  // T(silu(g)), fp32 math like torch
-      a[i] = Cvt<T>::rnd(__fmul_rn(s, u[i]));
+    const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(base) + v);
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + I) + v);
+    uint32_t row2 = 0, v2 = 0;
+    uint4 g1 = make_uint4(0, 0, 0, 0), u1 = g1;
+    if (idx2 < total) {
+      row2 = idx2 / vec_per_row;
+      v2 = idx2 - row2 * vec_per_row;
+      const T* base2 = gate_up + static_cast<size_t>(row2) * row_stride;
+      g1 = __ldg(reinterpret_cast<const uint4*>(base2) + v2);
+      u1 = __ldg(reinterpret_cast<const uint4*>(base2 + I) + v2);
     }
-    if (a_out != nullptr) reinterpret_cast<uint4*>(a_out + static_cast<size_t>(row) * I)[v] = pack8<T>(a);
-    if (q_out != nullptr) {
-      float t[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        t[i] = Cvt<T>::rnd(div_mode == ASQ_DIV_RECIPROCAL ? __fmul_rn(a[i], inv_quant_scale) : __fdiv_rn(a[i], quant_scale));
-      reinterpret_cast<uint2*>(q_out + static_cast<size_t>(row) * I)[v] =
-          make_uint2(s8x4(t[0], t[1], t[2], t[3]), s8x4(t[4], t[5], t[6], t[7]));
-    }
+    silu_mul_vec<T>(g0, u0, quant_scale, inv_quant_scale, div_mode,
+                    q_out ? q_out + static_cast<size_t>(row) * I + v * 8 : nullptr,
+                    a_out ? a_out + static_cast<size_t>(row) * I + v * 8 : nullptr);
+    if (idx2 < total)
+      silu_mul_vec<T>(g1, u1, quant_scale, inv_quant_scale, div_mode,
+                      q_out ? q_out + static_cast<size_t>(row2) * I + v2 * 8 : nullptr,
+                      a_out ? a_out + static_cast<size_t>(row2) * I + v2 * 8 : nullptr);
   }
 }
 
@@ -169,15 +209,16 @@ __global__ void __launch_bounds__(256) silu_mul_quant_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) rope_kernel(T* __restrict__ qk, long long row_stride, const T* __restrict__ cos_t,
                                                    const T* __restrict__ sin_t, int M, int S, int n_heads, int head_dim) {
-  const int half_vecs = head_dim / 16;  // 16-byte vectors in half a head
-  const long long total = static_cast<long long>(M) * n_heads * half_vecs;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(idx % half_vecs);
-    const long long hh = idx / half_vecs;
-    const int head = static_cast<int>(hh % n_heads);
-    const int row = static_cast<int>(hh / n_heads);
-    const int pos = row % S;
+  // 32-bit index arithmetic (the host checks the element count < 2^31)
+  const uint32_t half_vecs = static_cast<uint32_t>(head_dim) / 16u;  // 16-byte vectors in half a head
+  const uint32_t per_row = static_cast<uint32_t>(n_heads) * half_vecs;
+  const uint32_t total = static_cast<uint32_t>(M) * per_row;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t row = idx / per_row;
+    const uint32_t rem = idx - row * per_row;
+    const uint32_t head = rem / half_vecs;
+    const uint32_t v = rem - head * half_vecs;
+    const uint32_t pos = row % static_cast<uint32_t>(S);
     T* p = qk + static_cast<size_t>(row) * row_stride + static_cast<size_t>(head) * head_dim;
     uint4* lo_p = reinterpret_cast<uint4*>(p) + v;
     uint4* hi_p = reinterpret_cast<uint4*>(p + head_dim / 2) + v;
@@ -221,22 +262,25 @@ int asq_add_rmsnorm_quant(const void* x, const void* delta, const void* weight, 
                           int8_t* q_out, int dtype, int64_t M, int64_t H, float eps, void* stream) {
   using namespace asq_glue;
   if (dtype != ASQ_BF16 && dtype != ASQ_F16) return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: dtype must be f16 or bf16");
-  if (M < 0 || H <= 0 || H % 8 != 0 || H > 32 * 8 * NORM_MAXV)
-    return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: H=%lld must be a multiple of 8 and <= %d", (long long)H, 32 * 8 * NORM_MAXV);
+  if (M < 0 || H <= 0 || H % 8 != 0 || H > NORM_THREADS * 8 * NORM_MAXV)
+    return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: H=%lld must be a multiple of 8 and <= %d", (long long)H, NORM_THREADS * 8 * NORM_MAXV);
   if (M == 0) return ASQ_OK;
   if (x == nullptr || weight == nullptr || (h_out == nullptr && q_out == nullptr) || (delta != nullptr && x_out == nullptr))
     return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: null pointer argument");
   if (!aligned16(x) || !aligned16(weight) || !aligned16(delta) || !aligned16(x_out) || !aligned16(h_out) || !aligned16(q_out))
     return asq_glue_fail(ASQ_ERR_INVALID, "rmsnorm: pointers must be 16-byte aligned");
-  const int grid = grid_for(M, 8);
+  const int grid = static_cast<int>(M);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define ASQ_NORM_LAUNCH(TT, NVV)                                                                                   \
-  add_rmsnorm_quant_kernel<TT, NVV><<<grid, 256, 0, st>>>(static_cast<const TT*>(x), static_cast<const TT*>(delta),   \
-                                                          static_cast<const TT*>(weight), static_cast<TT*>(x_out),   \
-                                                          static_cast<TT*>(h_out), q_out, (int)M, (int)H, eps)
-  const bool small = H <= 32 * 8 * 16;
-  if (dtype == ASQ_BF16) { if (small) ASQ_NORM_LAUNCH(__nv_bfloat16, 16); else ASQ_NORM_LAUNCH(__nv_bfloat16, 32); }
-  else                   { if (small) ASQ_NORM_LAUNCH(__half, 16); else ASQ_NORM_LAUNCH(__half, 32); }
+#define ASQ_NORM_LAUNCH(TT, NVV)                                                                                        \
+  add_rmsnorm_quant_kernel<TT, NVV><<<grid, NORM_THREADS, 0, st>>>(static_cast<const TT*>(x), static_cast<const TT*>(delta), \
+                                                                   static_cast<const TT*>(weight), static_cast<TT*>(x_out), \
+                                                                   static_cast<TT*>(h_out), q_out, (int)M, (int)H, eps)
+  const int nv = static_cast<int>((H / 8 + NORM_THREADS - 1) / NORM_THREADS);
+  if (dtype == ASQ_BF16) {
+    if (nv <= 2) ASQ_NORM_LAUNCH(__nv_bfloat16, 2); else if (nv <= 4) ASQ_NORM_LAUNCH(__nv_bfloat16, 4); else ASQ_NORM_LAUNCH(__nv_bfloat16, 8);
+  } else {
+    if (nv <= 2) ASQ_NORM_LAUNCH(__half, 2); else if (nv <= 4) ASQ_NORM_LAUNCH(__half, 4); else ASQ_NORM_LAUNCH(__half, 8);
+  }
 #undef ASQ_NORM_LAUNCH
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ASQ_OK : asq_glue_fail(ASQ_ERR_CUDA, "rmsnorm launch failed: %s", cudaGetErrorString(e));
@@ -249,6 +293,7 @@ int asq_silu_mul_quant(const void* gate_up, int dtype, int64_t M, int64_t I, int
   if (M < 0 || I <= 0 || I % 8 != 0 || row_stride < 2 * I || row_stride % 8 != 0)
     return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: bad shape M=%lld I=%lld stride=%lld", (long long)M, (long long)I, (long long)row_stride);
   if (M == 0) return ASQ_OK;
+  if (M * (I / 8) >= (1ll << 31)) return asq_glue_fail(ASQ_ERR_UNSUPPORTED, "silu_mul: more than 2^31 vectors; split the batch");
   if (gate_up == nullptr || (q_out == nullptr && a_out == nullptr)) return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: null pointer argument");
   if (!aligned16(gate_up) || !aligned16(q_out) || !aligned16(a_out)) return asq_glue_fail(ASQ_ERR_INVALID, "silu_mul: pointers must be 16-byte aligned");
   const int grid = grid_for(M * (I / 8), 256);
@@ -271,6 +316,7 @@ int asq_rope_inplace(void* qk, int dtype, const void* cos_table, const void* sin
   if (M < 0 || S <= 0 || n_heads <= 0 || head_dim <= 0 || head_dim % 16 != 0 || row_stride < n_heads * head_dim || row_stride % 8 != 0)
     return asq_glue_fail(ASQ_ERR_INVALID, "rope: bad shape");
   if (M == 0) return ASQ_OK;
+  if (M * n_heads * (head_dim / 16) >= (1ll << 31)) return asq_glue_fail(ASQ_ERR_UNSUPPORTED, "rope: more than 2^31 vectors; split the batch");
   if (qk == nullptr || cos_table == nullptr || sin_table == nullptr) return asq_glue_fail(ASQ_ERR_INVALID, "rope: null pointer argument");
   if (!aligned16(qk) || !aligned16(cos_table) || !aligned16(sin_table)) return asq_glue_fail(ASQ_ERR_INVALID, "rope: pointers must be 16-byte aligned");
   const int grid = grid_for(M * n_heads * (head_dim / 16), 256);
