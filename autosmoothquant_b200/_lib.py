@@ -103,7 +103,7 @@ def load():
         lib.asq_w8a8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f,
                                         c_vp, c_vp, c_i, c_vp, c_sz, c_vp]
         lib.asq_fp8_linear.restype = c_i
-        lib.asq_fp8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f,
+        lib.asq_fp8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f, c_f,
                                        c_vp, c_i, c_vp, c_sz, c_vp]
         lib.asq_i8gemm_o32.restype = c_i
         lib.asq_i8gemm_o32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]
@@ -246,6 +246,7 @@ def fp8_linear(
     out_dtype: Optional[torch.dtype] = None,
     row_scale_out: Optional[torch.Tensor] = None,
     div_mode: Optional[int] = None,
+    out_scale: float = 0.0,
 ) -> torch.Tensor:
     """Fused quantise -> e4m3 GEMM (fp32 accumulate) -> scale (+bias); ``weight`` is float8_e4m3fn [N,K]."""
     global _launches
@@ -273,7 +274,7 @@ def fp8_linear(
         ws, ws_bytes = _workspace(dev, stream, need)
         rc = lib.asq_fp8_linear(
             x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
-            M, N, K, act_mode, float(in_scale), float(w_scale), _ptr(row_scale_out),
+            M, N, K, act_mode, float(in_scale), float(w_scale), float(out_scale), _ptr(row_scale_out),
             _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
         )
     _check(rc)

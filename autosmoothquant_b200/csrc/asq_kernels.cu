@@ -42,6 +42,8 @@ constexpr int BLOCK_K = 128;  // bytes == elements for 8-bit operands; one 128B 
 constexpr int UMMA_K = 32;    // K per tcgen05.mma for 8-bit operands
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int SYNC_AMAX = 8190;      // per-tensor dynamic: bit pattern of the running absmax (non-negative floats order like uints)
+constexpr int SYNC_AMAX_CNT = 8191;  // ... and the number of warps that contributed
 constexpr int SYNC_EXIT = 0;                          // sync[0]: CTAs that finished; sync[1+p]: rows ready in panel p
 
 enum EpiKind : int { EPI_DEQUANT = 0, EPI_RAW_I32 = 1, EPI_ALPHA_BETA = 2 };
@@ -70,6 +72,7 @@ struct LinearParams {
   const float* col_scale;
   const void* bias_any;  // EPI_ALPHA_BETA bias (int8 / int32 / fp32)
   float dequant_scale, alpha, beta;
+  float out_fq_scale, inv_out_fq_scale;  // != 0: fake-quantise the output through e4m3 (FP8LinearStatic, linear.py:562-564)
   int M, N, K;
   int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
   int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;  // num_n_blocks = TILE_N-wide tiles per row
@@ -204,6 +207,8 @@ __device__ __forceinline__ void quantize_vec(const uint4& v, uint8_t* dst, int m
                                                           : __fdiv_rn(f[i], scale);
     } else if (mode == ASQ_ACT_SCALE) {
       f[i] = Elem<T>::round_to(recip ? __fmul_rn(f[i], p.inv_quant_scale) : __fdiv_rn(f[i], p.quant_scale));
+    } else if (mode == ASQ_ACT_PER_TENSOR_DYNAMIC) {
+      f[i] = Elem<T>::round_to(__fdiv_rn(f[i], scale));  // T tensor / 0-dim T tensor: true division, rounded to T
     }
   }
   pack_store<FP8, VEC>(dst, f);
@@ -247,7 +252,7 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
   float scale = 0.f, inv_scale = 0.f;
   uint4 buf[QBATCH];
 
-  if (mode == ASQ_ACT_ROW_SCALE_GIVEN) scale = given_scale;
+  if (mode == ASQ_ACT_ROW_SCALE_GIVEN || mode == ASQ_ACT_PER_TENSOR_DYNAMIC) scale = given_scale;
   if (mode == ASQ_ACT_PER_TOKEN) {
     float amax = 0.f;
     if (K <= CHUNK) {  // whole row lives in registers: one HBM read
@@ -295,15 +300,55 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
 }
 
 template <bool FP8>
-__device__ __forceinline__ float quantize_row_any(const LinearParams& p, int row, int lane) {
+__device__ __forceinline__ float quantize_row_any(const LinearParams& p, int row, int lane, float tensor_scale = 0.f) {
   uint8_t* qrow = p.a_q + static_cast<size_t>(row) * p.K;
   const size_t off = static_cast<size_t>(row) * p.K;
-  const float given = (p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? __ldg(p.row_scale_in + row) : 0.f;
+  const float given = (p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? __ldg(p.row_scale_in + row) : tensor_scale;
   if (p.x_dtype == ASQ_BF16)
     return quantize_row<__nv_bfloat16, FP8>(reinterpret_cast<const __nv_bfloat16*>(p.x) + off, qrow, p.K, lane, p, given);
   if (p.x_dtype == ASQ_F16)
     return quantize_row<__half, FP8>(reinterpret_cast<const __half*>(p.x) + off, qrow, p.K, lane, p, given);
   return quantize_row<float, FP8>(reinterpret_cast<const float*>(p.x) + off, qrow, p.K, lane, p, given);
+}
+
+// Per-tensor DYNAMIC scale (per_tensor_quantize_fp8, quantization.py:144-170): s = T(max|x|) / T(448) over the
+// whole tensor.  Every participating warp folds the absmax of its rows into one global word (atomicMax on
+// the bit pattern), then all warps wait for each other — a grid-wide dependency, safe because the launch
+// never has more CTAs than can be co-resident.
+template <typename T>
+__device__ __forceinline__ float rows_absmax(const LinearParams& p, int first_row, int row_step, int lane) {
+  constexpr int VEC = Elem<T>::VEC;
+  float amax = 0.f;
+  for (int row = first_row; row < p.M; row += row_step) {
+    const T* xrow = reinterpret_cast<const T*>(p.x) + static_cast<size_t>(row) * p.K;
+#pragma unroll 8
+    for (int c = lane * VEC; c < p.K; c += 32 * VEC)
+      amax = vec_absmax<T>(__ldg(reinterpret_cast<const uint4*>(xrow + c)), amax);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  return amax;
+}
+
+__device__ __forceinline__ float tensor_scale_phase(const LinearParams& p, int first_row, int row_step,
+                                                    int participants, int lane) {
+  float amax = (p.x_dtype == ASQ_BF16) ? rows_absmax<__nv_bfloat16>(p, first_row, row_step, lane)
+               : (p.x_dtype == ASQ_F16) ? rows_absmax<__half>(p, first_row, row_step, lane)
+                                        : rows_absmax<float>(p, first_row, row_step, lane);
+  uint32_t bits = 0;
+  if (lane == 0) {
+    atomicMax(p.sync + SYNC_AMAX, __float_as_uint(amax));
+    red_release_gpu_add(p.sync + SYNC_AMAX_CNT, 1u);
+    while (ld_acquire_gpu(p.sync + SYNC_AMAX_CNT) < static_cast<uint32_t>(participants)) __nanosleep(128);
+    bits = ld_acquire_gpu(p.sync + SYNC_AMAX);
+  }
+  bits = __shfl_sync(0xffffffffu, bits, 0);
+  amax = __uint_as_float(bits);
+  const bool recip = (p.div_mode == ASQ_DIV_RECIPROCAL);
+  const float s = recip ? __fmul_rn(amax, p.inv_qmax) : __fdiv_rn(amax, p.qmax);  // tensor / python float, in T
+  if (p.x_dtype == ASQ_BF16) return Elem<__nv_bfloat16>::round_to(s);
+  if (p.x_dtype == ASQ_F16) return Elem<__half>::round_to(s);
+  return s;
 }
 
 // ------------------------------------------------------------------ epilogue
@@ -339,6 +384,12 @@ __device__ __forceinline__ void load_cols32(const float* __restrict__ src, int c
   }
 }
 
+__device__ __forceinline__ float round_out(float v, int y_dtype) {
+  if (y_dtype == ASQ_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (y_dtype == ASQ_F16) return __half2float(__float2half_rn(v));
+  return v;
+}
+
 // Raw accumulators r[32] (row `row`, columns col0..col0+31) -> fp32 results v[32] following the reference's
 // order of operations (linear.py:93,104 / :197-207): factor first, then * acc, then + bias, each a separate
 // fp32 rounding (no FMA contraction), so the result is bit-identical to eager torch.
@@ -347,7 +398,8 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (
                                                 const LinearParams& p) {
   const int N = p.N;
   if (p.epi_kind == EPI_DEQUANT) {
-    const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN);
+    const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN ||
+                            p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC);
     const float f_scalar = per_token ? __fmul_rn(p.dequant_scale, rs) : p.dequant_scale;
     if (p.col_scale != nullptr) {
       float cs[32];
@@ -370,6 +422,22 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (
       load_cols32(p.bias, col0, N, b);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(v[j], b[j]);
+    }
+    if (p.out_fq_scale != 0.f) {
+      // FP8LinearStatic output fake-quantisation (linear.py:562-564): y = T(e4m3(clamp(T(T(v) / os))) * os)
+      const bool recip = (p.div_mode == ASQ_DIV_RECIPROCAL);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float t0 = round_out(v[j], p.y_dtype), t1 = round_out(v[j + 1], p.y_dtype);
+        t0 = round_out(recip ? __fmul_rn(t0, p.inv_out_fq_scale) : __fdiv_rn(t0, p.out_fq_scale), p.y_dtype);
+        t1 = round_out(recip ? __fmul_rn(t1, p.inv_out_fq_scale) : __fdiv_rn(t1, p.out_fq_scale), p.y_dtype);
+        const uint32_t q2 = cvt_e4m3x2(t0, t1);
+        uint32_t h2;
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(static_cast<uint16_t>(q2)));
+        const float2 d = __half22float2(*reinterpret_cast<__half2*>(&h2));
+        v[j] = __fmul_rn(d.x, p.out_fq_scale);  // the final rounding to T happens in the store
+        v[j + 1] = __fmul_rn(d.y, p.out_fq_scale);
+      }
     }
   } else {  // EPI_ALPHA_BETA: v = alpha*acc + beta*bias  (cublasLt o8 / csrc/kernels/linear.cu epilogues)
 #pragma unroll
@@ -679,9 +747,11 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ew = warp - 2;  // 0..7
     if (fused) {
       const int warps_total = NUM_EPI_WARPS * gridDim.x;
+      const bool tensor_dyn = (p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC);
+      const float ts = tensor_dyn ? tensor_scale_phase(p, ew * gridDim.x + blockIdx.x, warps_total, warps_total, lane) : 0.f;
       for (int row = ew * gridDim.x + blockIdx.x; row < p.M; row += warps_total) {
-        const float s = quantize_row_any<FP8>(p, row, lane);
-        if (lane == 0 && (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN)) {
+        const float s = quantize_row_any<FP8>(p, row, lane, ts);
+        if (lane == 0 && (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN || tensor_dyn)) {
           p.row_scale[row] = s;
           if (p.row_scale_out != nullptr) p.row_scale_out[row] = s;
         }
@@ -701,8 +771,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
     const bool staged = p.tma_store != 0;
     const int elem = out16 ? 2 : 4;
-    const bool per_token_epi = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) &&
-                               p.epi_kind == EPI_DEQUANT;
+    const bool per_token_epi = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN ||
+                                p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC) && p.epi_kind == EPI_DEQUANT;
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     int it = 0;
     TileWalk walk(p, worker, num_workers);
@@ -810,6 +880,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (done == gridDim.x - 1) {
       const int panels = (p.M + BLOCK_M - 1) / BLOCK_M;
       for (int i = 0; i < panels; ++i) p.sync[1 + i] = 0u;
+      p.sync[SYNC_AMAX] = 0u;
+      p.sync[SYNC_AMAX_CNT] = 0u;
       p.sync[SYNC_EXIT] = 0u;
       __threadfence();
     }
@@ -1074,21 +1146,21 @@ bool is_float_dtype(int d) { return d == ASQ_F32 || d == ASQ_F16 || d == ASQ_BF1
 int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype,
                  int64_t M, int64_t N, int64_t K, int act_mode, float quant_scale, float dequant_scale,
                  const float* col_scale, float* row_scale_out, int div_mode, void* workspace,
-                 size_t workspace_bytes, void* stream) {
+                 size_t workspace_bytes, void* stream, float out_fq_scale = 0.f) {
   int rc = check_common(x, w, y, M, N, K);
   if (rc != ASQ_OK) return rc;
   if (!is_float_dtype(x_dtype) || !is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "x/y dtype must be f32, f16 or bf16");
   if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
-  if (act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC)
-    return fail(ASQ_ERR_UNSUPPORTED, "per-tensor dynamic activation scale is not implemented in the fused kernel");
+  if (act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC && !fp8)
+    return fail(ASQ_ERR_UNSUPPORTED, "per-tensor dynamic activation scale exists for the fp8 path only (quantization.py:144-170)");
   if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN &&
-      act_mode != ASQ_ACT_ROW_SCALE_GIVEN)
+      act_mode != ASQ_ACT_ROW_SCALE_GIVEN && act_mode != ASQ_ACT_PER_TENSOR_DYNAMIC)
     return fail(ASQ_ERR_INVALID, "bad act_mode %d", act_mode);
   if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN && row_scale_out == nullptr && M > 0)
     return fail(ASQ_ERR_INVALID, "ASQ_ACT_ROW_SCALE_GIVEN needs the [M] row scales in row_scale");
   if (fp8 && act_mode == ASQ_ACT_ROUND) return fail(ASQ_ERR_INVALID, "ASQ_ACT_ROUND is int8-only");
   if (M == 0) return ASQ_OK;
-  if ((M + asq::BLOCK_M - 1) / asq::BLOCK_M + 1 > static_cast<int64_t>(kSyncBytes / 4))
+  if ((M + asq::BLOCK_M - 1) / asq::BLOCK_M + 1 > static_cast<int64_t>(kSyncBytes / 4) - 2)
     return fail(ASQ_ERR_UNSUPPORTED, "M=%lld exceeds the %zu row panels one launch tracks; split the batch", (long long)M, kSyncBytes / 4 - 1);
   if (workspace == nullptr || workspace_bytes < asq_workspace_bytes(M, K))
     return fail(ASQ_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", asq_workspace_bytes(M, K), workspace_bytes);
@@ -1107,6 +1179,8 @@ int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const floa
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.x_dtype = x_dtype; p.y_dtype = y_dtype; p.act_mode = act_mode; p.div_mode = div_mode;
   p.epi_kind = asq::EPI_DEQUANT;
+  p.out_fq_scale = out_fq_scale;
+  p.inv_out_fq_scale = out_fq_scale != 0.f ? 1.0f / out_fq_scale : 0.f;
   return launch_linear(fp8, ws.a_q, w, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -1139,12 +1213,12 @@ int asq_w8a8_linear(const void* x, int x_dtype, const int8_t* w, const float* bi
 }
 
 int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const float* bias, void* y, int y_dtype,
-                   int64_t M, int64_t N, int64_t K, int act_mode, float in_scale, float w_scale,
+                   int64_t M, int64_t N, int64_t K, int act_mode, float in_scale, float w_scale, float out_scale,
                    float* row_scale_out, int div_mode, void* workspace, size_t workspace_bytes, void* stream) {
-  // per-token: y = acc * (w_scale * s[m]); static: y = acc * (w_scale * in_scale)
-  const float ds = (act_mode == ASQ_ACT_PER_TOKEN || act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? w_scale : w_scale * in_scale;
+  // dynamic scales live in the row-scale vector: y = acc * (w_scale * s[m]); static: y = acc * (w_scale * in_scale)
+  const float ds = (act_mode == ASQ_ACT_SCALE) ? w_scale * in_scale : w_scale;
   return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, in_scale, ds, nullptr,
-                      row_scale_out, div_mode, workspace, workspace_bytes, stream);
+                      row_scale_out, div_mode, workspace, workspace_bytes, stream, out_scale);
 }
 
 int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,

@@ -328,14 +328,11 @@ class FP8LinearStatic(_FP8Base):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x2 = x.reshape(-1, self.in_features)
+        # a truthy output_scale additionally fake-quantises the output through e4m3 (reference :562-564);
+        # the kernel epilogue does it in place of the two extra eager launches
+        out_scale = 0.0 if self.output_scale is None else _scalar(self.output_scale)
         y = _lib.fp8_linear(x2, self.weight, self._bias_f32(), _lib.ACT_SCALE, _scalar(self.input_scale),
-                            _scalar(self.weight_scale))
-        out_scale = None if self.output_scale is None else _scalar(self.output_scale)
-        if out_scale:
-            raise NotImplementedError(
-                "FP8LinearStatic with a non-zero output_scale (output fake-quantisation, reference :562-564) "
-                "is not implemented; set output_scale to 0 to disable it as the reference does"
-            )
+                            _scalar(self.weight_scale), out_scale=out_scale)
         return y.view(*x.shape[:-1], self.out_features)
 
     @staticmethod

@@ -125,10 +125,16 @@ int asq_w8a8_linear(const void* x, int x_dtype, const int8_t* w, const float* bi
 /* FP8-e4m3 twin: y = T( (sum_k q[m,k]*w[n,k]) * (s_x * w_scale) (+ bias) ), fp32 accumulate
  * on the tensor cores (the reference dequantises both operands and calls F.linear,
  * linear.py:363-368).
- *   w  [N,K] e4m3 bytes;  act_mode in {SCALE (static, in_scale), PER_TOKEN, PER_TENSOR_DYNAMIC} */
+ *   w  [N,K] e4m3 bytes
+ *   act_mode  ASQ_ACT_PER_TOKEN (FP8LinearDynamic per-token), ASQ_ACT_SCALE (FP8LinearStatic, in_scale),
+ *             ASQ_ACT_PER_TENSOR_DYNAMIC (FP8LinearDynamic's other branch: whole-tensor absmax, computed
+ *             in-kernel with a grid-wide reduction), ASQ_ACT_ROW_SCALE_GIVEN
+ *   out_scale != 0: the output is additionally fake-quantised through e4m3 with this scale
+ *             (FP8LinearStatic with a truthy output_scale, linear.py:562-564)
+ *   row_scale_out [M] or NULL receives the activation scale used for every row */
 int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const float* bias,
                    void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                   int act_mode, float in_scale, float w_scale,
+                   int act_mode, float in_scale, float w_scale, float out_scale,
                    float* row_scale_out, int div_mode,
                    void* workspace, size_t workspace_bytes, void* stream);
 

@@ -192,6 +192,38 @@ def main() -> None:
             add(f"c{cid}", "fp8_linear", **kw)
             cid += 1
 
+    # ---- FP8LinearDynamic per-tensor dynamic branch (linear.py:417-418) and FP8LinearStatic with output
+    #      fake-quantisation (linear.py:562-564)
+    for dname in ("f32", "bf16"):
+        dtype = DTYPES[dname]
+        K, N = 64, 40
+        wf = torch.randn(N, K, generator=gen) * 0.05
+        wq, wscale = ref_quant.per_tensor_quantize_fp8(wf)
+        bias = torch.randn(N, generator=gen)
+        x = make_x(gen, (11, K), dtype, zero_row=False)
+        mod = ref_linear.FP8LinearDynamic(K, N, "per-tensor", True)
+        mod.weight = wq
+        mod.weight_scale = wscale.to(torch.float32)
+        mod.bias = bias.to(dtype)
+        y = mod(x)
+        add(f"c{cid}", "fp8_linear", x=f32(x), w=wq.view(torch.uint8).numpy().copy(), y=f32(y), w_scale=float(wscale),
+            act="per-tensor", dtype=dname, bias=f32(bias.to(dtype)))
+        cid += 1
+    for out_scale in (0.031, 0.2):
+        K, N = 64, 40
+        wf = torch.randn(N, K, generator=gen) * 0.05
+        wq, wscale = ref_quant.per_tensor_quantize_fp8(wf)
+        x = make_x(gen, (11, K), torch.float32, zero_row=False)
+        mod = ref_linear.FP8LinearStatic(K, N, False)
+        mod.weight = wq
+        mod.weight_scale = wscale.to(torch.float32)
+        mod.input_scale = torch.tensor(float(x.abs().max() / 448.0))
+        mod.output_scale = torch.tensor(out_scale)
+        y = mod(x)
+        add(f"c{cid}", "fp8_linear", x=f32(x), w=wq.view(torch.uint8).numpy().copy(), y=f32(y), w_scale=float(wscale),
+            act="static", in_scale=float(mod.input_scale), out_scale=out_scale, dtype="f32")
+        cid += 1
+
     np.savez_compressed(OUT_DIR / "w8a8_golden.npz", **arrays)
     (OUT_DIR / "w8a8_golden.json").write_text(json.dumps(meta, indent=1))
     size = (OUT_DIR / "w8a8_golden.npz").stat().st_size

@@ -36,7 +36,8 @@ E4M3_MAX = 448.0
 # ----------------------------------------------------------------------------- dtype rounding
 def round_to_bf16(v: np.ndarray) -> np.ndarray:
     """fp32 -> bf16 (round to nearest even) -> fp32."""
-    v = np.ascontiguousarray(v, dtype=F32)
+    shape = np.shape(v)
+    v = np.ascontiguousarray(v, dtype=F32).reshape(-1)
     u = v.view(np.uint32).astype(np.uint64)
     bias = 0x7FFF + ((u >> 16) & 1)
     r = ((u + bias) & 0xFFFF0000).astype(np.uint32)
@@ -44,7 +45,7 @@ def round_to_bf16(v: np.ndarray) -> np.ndarray:
     nan = np.isnan(v)
     if nan.any():
         out[nan] = np.nan
-    return out.reshape(v.shape)
+    return out.reshape(shape)
 
 
 def round_to(v: np.ndarray, dtype: str) -> np.ndarray:
@@ -145,9 +146,9 @@ def quantize_per_tensor_absmax(w: np.ndarray, dtype: str = "f32") -> Tuple[np.nd
     then ``div_(scale).round_()`` and ``.to(int8)`` without a clamp.
     """
     w = np.asarray(w, dtype=F32)
-    scale = round_to(np.abs(w).max() / F32(127), dtype)  # 0-dim tensor in W's dtype
-    q = np.rint(w / F32(scale))
-    return q.astype(np.int8), F32(scale)
+    scale = F32(round_to(np.abs(w).max() / F32(127), dtype).reshape(()))  # 0-dim tensor in W's dtype
+    q = np.rint(w / scale)
+    return q.astype(np.int8), scale
 
 
 # ----------------------------------------------------------------------------- activation quant
@@ -302,23 +303,27 @@ def fp8_linear_exact(
 
 def fp8_linear_reference_math(
     x: np.ndarray, dtype: str, w_bytes: np.ndarray, w_scale: float, act_quant: str = "per-token",
-    in_scale: float = 1.0, bias: Optional[np.ndarray] = None, div_mode: str = "exact",
+    in_scale: float = 1.0, bias: Optional[np.ndarray] = None, div_mode: str = "exact", out_scale: float = 0.0,
 ) -> np.ndarray:
-    """FP8LinearDynamic / FP8LinearStatic forward as the reference computes it on fp32 activations
-    (easy_fp8_gemm, linear.py:336-369): ``F.linear(A.to(dt) * sA, W.to(dt) * sW, bias)`` with an fp32
-    GEMM.  Only meaningful for dtype='f32' (the reference raises a dtype mismatch for per-token fp16/bf16
-    inputs); the accumulation order of a BLAS GEMM is not pinned, so compare with a
-    tolerance."""
+    """FP8LinearDynamic / FP8LinearStatic forward as the reference computes it (easy_fp8_gemm,
+    linear.py:336-369): ``F.linear(A.to(dt) * sA, W.to(dt) * sW, bias)`` in the activation dtype, optionally
+    followed by the output fake-quantisation of FP8LinearStatic (linear.py:562-564).  The reference raises a
+    dtype mismatch for per-token fp16/bf16 inputs, so per-token is fp32-only; the
+    accumulation order of a BLAS GEMM is not pinned, so compare with a tolerance."""
     x = np.asarray(x, dtype=F32)
     mode = {"per-token": "per-token", "static": "scale", "per-tensor": "per-tensor"}[act_quant]
     q, s = quantize_act_fp8(x.reshape(-1, x.shape[-1]), dtype, mode, in_scale, div_mode)
     a_scale = F32(in_scale) if mode == "scale" else s
-    a = (e4m3_decode(q) * np.asarray(a_scale, F32).reshape(-1, 1)).astype(F32)
-    w = (e4m3_decode(w_bytes) * F32(w_scale)).astype(F32)
-    y = a @ w.T
+    a = round_to(e4m3_decode(q) * np.asarray(a_scale, F32).reshape(-1, 1), dtype)
+    w = round_to(e4m3_decode(w_bytes) * F32(w_scale), dtype)
+    y = a.astype(np.float64) @ w.astype(np.float64).T
     if bias is not None:
-        y = y + np.asarray(bias, F32)
-    return y.astype(F32).reshape(*x.shape[:-1], w_bytes.shape[0])
+        y = y + np.asarray(bias, np.float64)
+    y = round_to(y.astype(F32), dtype)
+    if out_scale:
+        t = _scalar_div(y, out_scale, dtype, div_mode)
+        y = round_to(e4m3_decode(e4m3_encode(np.clip(t, -E4M3_MAX, E4M3_MAX))) * F32(out_scale), dtype)
+    return y.reshape(*x.shape[:-1], w_bytes.shape[0])
 
 
 # ----------------------------------------------------------------------------- tensor-parallel restatement

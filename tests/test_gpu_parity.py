@@ -109,7 +109,7 @@ def test_golden_fp8_quantisers(golden, exact_div):
 def test_golden_fp8_linear(golden, exact_div):
     """Tensor-core fp32 accumulation vs the reference's dequantise + fp32 GEMM: both approximate the fp64
     value; tolerance = K * 2^-24 * sum|terms| (bounded here by 2e-5 of the output scale)."""
-    for c in (c for c in golden if c["kind"] == "fp8_linear"):
+    for c in (c for c in golden if c["kind"] == "fp8_linear" and c["act"] != "per-tensor" and "out_scale" not in c):
         N, K = c["w"].shape
         if c["act"] == "per-token":
             mod = NN.FP8LinearDynamic(K, N, "per-token", "bias" in c)
@@ -437,3 +437,104 @@ def test_glue_stack_close_to_module_stack():
         assert ya.shape == yb.shape and torch.isfinite(yb).all()
         assert float((ya - yb).abs().max()) <= 0.05 * float(ya.abs().max())
         assert float((ya != yb).float().mean()) < 0.5
+
+
+# ----------------------------------------------------------------------------- FP8: remaining reference branches
+def test_golden_fp8_per_tensor_dynamic_and_output_fakequant(golden, exact_div):
+    """FP8LinearDynamic's per-tensor branch (whole-tensor absmax reduced in-kernel, linear.py:417-418) and
+    FP8LinearStatic with a truthy output_scale (epilogue fake-quantisation, linear.py:562-564) against the
+    reference's recorded outputs."""
+    n = 0
+    for c in (c for c in golden if c["kind"] == "fp8_linear" and (c["act"] == "per-tensor" or "out_scale" in c)):
+        N, K = c["w"].shape
+        dt = TORCH_DT[c["dtype"]]
+        if c["act"] == "per-tensor":
+            mod = NN.FP8LinearDynamic(K, N, "per-tensor", "bias" in c)
+        else:
+            mod = NN.FP8LinearStatic(K, N, "bias" in c)
+            mod.input_scale = torch.tensor(c["in_scale"], dtype=torch.float32)
+            mod.output_scale = torch.tensor(c["out_scale"], dtype=torch.float32)
+        mod.weight = torch.from_numpy(c["w"]).view(torch.float8_e4m3fn)
+        mod.weight_scale = torch.tensor(c["w_scale"], dtype=torch.float32)
+        if "bias" in c:
+            mod.bias = torch.from_numpy(c["bias"])
+        mod = mod.to(DEV)
+        y = mod(t(c["x"], dt)).float().cpu().numpy()
+        scale = np.abs(c["y"]).max()
+        if "out_scale" in c:
+            # outputs live on the e4m3 grid (times out_scale): a value may land on a neighbouring code
+            assert np.mean(y != c["y"]) < 0.02 and np.abs(y - c["y"]).max() <= 0.13 * scale, c["id"]
+            grid = O.e4m3_decode(np.arange(256, dtype=np.uint8))
+            grid = grid[np.isfinite(grid)] * np.float32(c["out_scale"])
+            assert np.isin(y, grid).all()
+        else:
+            tol = 2e-5 if c["dtype"] == "f32" else 2 ** -7
+            np.testing.assert_allclose(y, c["y"], rtol=0, atol=tol * scale, err_msg=c["id"])
+        n += 1
+    assert n == 4
+
+
+def test_fp8_per_tensor_dynamic_scale_is_the_oracle_scale(exact_div):
+    rng = np.random.default_rng(2)
+    M, N, K = 700, 264, 528
+    x = make_x(rng, M, K, "bf16")
+    w = O.e4m3_encode(np.clip(rng.standard_normal((N, K)).astype(np.float32) * 20, -448, 448))
+    rs = torch.empty(M, dtype=torch.float32, device=DEV)
+    for _ in range(2):  # second launch re-uses the (restored) reduction words
+        y = L.fp8_linear(t(x, torch.bfloat16), t(w).view(torch.float8_e4m3fn), None, L.ACT_PER_TENSOR_DYNAMIC, 1.0, 0.01,
+                         row_scale_out=rs)
+    q, s = O.quantize_act_fp8(x, "bf16", "per-tensor")
+    assert torch.all(rs == float(np.asarray(s).reshape(()))).item()
+    want = O.fp8_linear_exact(q, w, np.full(M, float(np.asarray(s).reshape(())), np.float32), 0.01)
+    ok = np.isfinite(want)
+    got = y.float().cpu().numpy()
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2 ** -7, atol=2 ** -7 * np.abs(want[ok]).max())
+
+
+# ----------------------------------------------------------------------------- BASELINE configs 3-5: per-rank shapes
+@pytest.mark.parametrize("name,M,N,K,act", [
+    ("13B o_proj per-token", 4096, 5120, 5120, "per-token"),
+    ("13B down_proj per-token", 4096, 5120, 13824, "per-token"),
+    ("13B qkv per-tensor (batch-32 prefill slice)", 8192, 15360, 5120, "per-tensor"),
+    ("Mixtral TP8 w1|w3 per-token", 512, 3584, 4096, "per-token"),
+    ("Mixtral TP8 w2 per-token (row shard)", 512, 4096, 1792, "per-token"),
+    ("Mixtral expert with 3 tokens", 3, 4096, 1792, "per-token"),
+])
+def test_config_shapes_int8_composition(name, M, N, K, act):
+    """Shapes of BASELINE configs 3 and 4 (per rank): fused output == reference epilogue applied to the exact
+    int32 GEMM of the prologue tap (each tap is oracle-checked bit-for-bit at small sizes), plus the integer
+    checksum-of-checksums of the GEMM."""
+    gen = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=gen).to(torch.bfloat16).to(DEV)
+    w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=gen).to(DEV)
+    mode = L.ACT_PER_TOKEN if act == "per-token" else L.ACT_ROUND
+    if act == "per-tensor":
+        x = (x.float() * 40).to(torch.bfloat16)
+    q, s = L.quantize_act(x, mode)
+    acc = torch.empty((M, N), dtype=torch.int32, device=DEV)
+    L.i8gemm_o32(q, w, acc)
+    assert torch.equal(acc.to(torch.int64).sum(dim=1), (q.to(torch.int64) * w.to(torch.int64).sum(dim=0)).sum(dim=1)), name
+    ds = 0.0021
+    y = L.w8a8_linear(x, w, None, mode, 1.0, ds)
+    want = ((ds * s.view(-1, 1)) * acc if s is not None else ds * acc).to(torch.bfloat16)
+    assert torch.equal(y, want), name
+
+
+@pytest.mark.parametrize("name,M,N,K", [
+    ("70B TP8 q_proj", 2048, 1024, 8192), ("70B TP8 kv_proj", 2048, 128, 8192), ("70B TP8 gate|up", 2048, 7168, 8192),
+    ("70B TP8 o_proj (row shard)", 2048, 8192, 1024), ("70B TP8 down_proj (row shard)", 2048, 8192, 3584),
+])
+def test_config5_shapes_fp8_per_token(name, M, N, K):
+    """BASELINE config 5 (Llama-2-70B FP8-e4m3 per-token, TP=8) per-rank shapes: tensor-core result vs an fp64
+    evaluation of the same quantised operands (the prologue tap is bit-exact vs the oracle at small sizes)."""
+    gen = torch.Generator(device="cpu").manual_seed(N + K)
+    x = torch.randn(M, K, generator=gen).to(torch.bfloat16).to(DEV)
+    wf = torch.randn(N, K, generator=gen) * 0.02
+    ws = float(wf.abs().max() / 448.0)
+    w = (wf / ws).clamp(-448, 448).to(torch.float8_e4m3fn).to(DEV)
+    y = L.fp8_linear(x, w, None, L.ACT_PER_TOKEN, 1.0, ws)
+    q, s = L.quantize_act(x, L.ACT_PER_TOKEN, fp8=True)
+    want = (q.double() @ w.double().t()) * (s.double().view(-1, 1) * ws)
+    err = (y.double() - want).abs().max().item()
+    # bf16 output rounding (2^-9 relative) + fp32 accumulation over K terms
+    assert err <= want.abs().max().item() * (2 ** -8 + K * 2 ** -24), name

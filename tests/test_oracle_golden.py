@@ -70,21 +70,31 @@ def test_fp8_quantisers_bit_exact(golden, kind, mode):
         if kind == "fp8_per_token":
             np.testing.assert_array_equal(s, c["scale"], err_msg=c["id"])
         elif kind == "fp8_per_tensor":
-            assert float(s) == c["scale"], c["id"]
+            assert float(np.asarray(s).reshape(())) == c["scale"], c["id"]
 
 
 def test_fp8_linear_reference_math(golden):
-    """The reference's fp8 forward is dequantise + fp32 GEMM; BLAS summation order is not pinned, so the
-    tolerance is K * eps_fp32 * sum|terms| (here: 1e-5 relative to the output scale)."""
+    """The reference's fp8 forward is dequantise + GEMM in the activation dtype; BLAS summation order is not
+    pinned, so the tolerance is 1e-5 of the output scale for fp32 and 2 ulp for bf16.  Output fake-quantisation
+    snaps values to the e4m3 grid, so there a handful of values may land on a neighbouring code."""
+    seen = set()
     for c in _cases(golden, "fp8_linear"):
-        act = "per-token" if c["act"] == "per-token" else "static"
-        y = O.fp8_linear_reference_math(c["x"], "f32", c["w"], c["w_scale"], act_quant=act,
-                                        in_scale=c.get("in_scale", 1.0), bias=c.get("bias"), div_mode="exact")
+        act = c["act"]
+        seen.add((act, c["dtype"], "out_scale" in c))
+        y = O.fp8_linear_reference_math(c["x"], c["dtype"], c["w"], c["w_scale"], act_quant=act,
+                                        in_scale=c.get("in_scale", 1.0), bias=c.get("bias"), div_mode="exact",
+                                        out_scale=c.get("out_scale", 0.0))
         scale = np.abs(c["y"]).max()
-        np.testing.assert_allclose(y, c["y"], rtol=0, atol=1e-5 * scale, err_msg=c["id"])
-        # and the fp64 evaluation of the same quantised operands agrees to fp32 accumulation error
-        mode = "per-token" if act == "per-token" else "scale"
-        q, s = O.quantize_act_fp8(c["x"], "f32", mode, c.get("in_scale", 1.0))
-        a_scale = s if mode == "per-token" else np.full(c["x"].shape[0], c["in_scale"], np.float32)
-        y64 = O.fp8_linear_exact(q, c["w"], a_scale, c["w_scale"], c.get("bias"))
-        np.testing.assert_allclose(y64, c["y"], rtol=0, atol=1e-5 * scale, err_msg=c["id"])
+        if "out_scale" in c:
+            assert np.mean(y != c["y"]) < 0.02 and np.abs(y - c["y"]).max() <= 0.13 * scale, c["id"]
+            continue
+        tol = 1e-5 if c["dtype"] == "f32" else 2 ** -7
+        np.testing.assert_allclose(y, c["y"], rtol=0, atol=tol * scale, err_msg=c["id"])
+        if c["dtype"] == "f32" and act != "per-tensor":
+            # and the fp64 evaluation of the same quantised operands agrees to fp32 accumulation error
+            mode = "per-token" if act == "per-token" else "scale"
+            q, s = O.quantize_act_fp8(c["x"], "f32", mode, c.get("in_scale", 1.0))
+            a_scale = s if mode == "per-token" else np.full(c["x"].shape[0], c["in_scale"], np.float32)
+            y64 = O.fp8_linear_exact(q, c["w"], a_scale, c["w_scale"], c.get("bias"))
+            np.testing.assert_allclose(y64, c["y"], rtol=0, atol=1e-5 * scale, err_msg=c["id"])
+    assert ("per-tensor", "bf16", False) in seen and ("static", "f32", True) in seen
