@@ -221,15 +221,22 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     k = k.view(B, S, nk, hd).transpose(1, 2)
     v = v.view(B, S, nv, hd).transpose(1, 2)
     attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=nk != nq)
+    # o_proj: the module quantises the attention output in-kernel; under tensor parallelism it is the
+    # row-parallel wrapper, whose forward ends with the all-reduce
     o = layer.o_proj(attn.transpose(1, 2).reshape(B * S, nq * hd))
     x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
     gu_mod = layer.gate_up_proj
     gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
                              col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
-    down = layer.down_proj
+    tp_world = getattr(layer, "tp_world", 1)
+    down = layer.down_proj.shard if tp_world > 1 else layer.down_proj
     a8, _ = _lib.silu_mul_quant(gu, float(down.quant_scale.item()))
     d = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
                             out_dtype=x2.dtype)
+    if tp_world > 1:  # row-parallel partial sums -> one all-reduce over NVLink
+        import torch.distributed as dist
+
+        dist.all_reduce(d, op=dist.ReduceOp.SUM, group=layer.tp_group)
     return x2, d
 
 

@@ -174,23 +174,56 @@ class RowParallelLinear(nn.Module):
         return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
 
 
+def _shard_fused_columns(fused, rank: int, world: int, device):
+    """Column shard of a fused W_pack module (q|k|v or gate|up): every block is split separately so rank r
+    holds [q_r; k_r; v_r] (its own heads) and the per-block dequant scales stay valid."""
+    from .layers.nn.linear import W8A8BFP32OFP32QKVLinear
+
+    sizes = fused.qkv_size
+    local_sizes, rows = [], []
+    start = 0
+    for n in sizes:
+        if n % world:
+            raise ValueError(f"block of {n} output features is not divisible by world {world}")
+        step = n // world
+        rows.append(fused.weight[start + rank * step:start + (rank + 1) * step])
+        local_sizes.append(step)
+        start += n
+    out = W8A8BFP32OFP32QKVLinear(local_sizes, fused.in_features, sum(local_sizes), fused.use_bias, fused.act_quant)
+    out.weight = torch.cat(rows, dim=0).contiguous()
+    for name in fused._scale_names:
+        setattr(out, name, getattr(fused, name).clone())
+    if fused.use_bias:
+        start, parts = 0, []
+        for n in sizes:
+            step = n // world
+            parts.append(fused.bias[start + rank * step:start + (rank + 1) * step])
+            start += n
+        out.bias = torch.cat(parts).contiguous()
+    return out.to(device)
+
+
 def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: Optional[Dict[str, str]] = None,
-                     group=None, dtype=torch.bfloat16, seed: int = 0):
-    """The benchmark stack of ``harness.QuantDecoder`` with every projection tensor-parallel: q/k/v/gate/up
-    column-sharded, o/down row-sharded (+ all-reduce), attention over the local heads."""
+                     group=None, dtype=torch.bfloat16, seed: int = 0, glue: bool = True):
+    """The benchmark stack of ``harness.QuantDecoder`` tensor-parallel over `world` ranks: fused q|k|v and
+    gate|up column-sharded by head / by intermediate channel, o_proj and down_proj row-sharded with ONE
+    all-reduce each (NCCL over NVLink), attention over the local heads, residual stream and norms replicated.
+    Every rank builds the same seeded full-size layer and keeps its shard (one layer at a time)."""
     from . import harness
 
-    model = harness.QuantDecoder(cfg, quant_config, device=device, dtype=dtype, seed=seed, layers=layers)
+    model = harness.QuantDecoder(cfg, quant_config, device=device, dtype=dtype, seed=seed, layers=layers,
+                                 fuse_projections=True, glue=glue)
     if model.qcfg["type"] != "int8":
         raise NotImplementedError("tensor-parallel fp8 stack")
     for layer in model.layers:
-        for name in ("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj"):
-            full = getattr(layer, name)
-            setattr(layer, name, ColumnParallelLinear(shard_column(full, rank, world).to(device)))
+        layer.qkv_proj = _shard_fused_columns(layer.qkv_proj, rank, world, device)
+        layer.qkv_sizes = list(layer.qkv_proj.qkv_size)
+        layer.gate_up_proj = _shard_fused_columns(layer.gate_up_proj, rank, world, device)
         for name in ("o_proj", "down_proj"):
             full = getattr(layer, name)
             setattr(layer, name, RowParallelLinear(shard_row(full, rank, world).to(device), group=group,
                                                    has_bias=full.use_bias))
-        layer.tp_world = world
+        layer.tp_world, layer.tp_group = world, group
+        torch.cuda.empty_cache()
     model.tp_world = world
     return model

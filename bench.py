@@ -198,7 +198,7 @@ def run_ours(args, cfg, layers):
     if args.parallel == "tp" and world > 1:
         from autosmoothquant_b200.tp import build_tp_decoder
 
-        model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank)
+        model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank, glue=not args.no_glue)
         batch = args.batch * world  # weak scaling: the global batch grows with the GPU count
     else:
         model = QuantDecoder(cfg, device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
@@ -232,7 +232,7 @@ def run_ours(args, cfg, layers):
         print(json.dumps({"profiled_step": True, "launches_per_step": launches_per_step}))
         return
     graph = None
-    use_graph = not args.no_graph and not (args.parallel == "tp" and world > 1)
+    use_graph = not args.no_graph
     if use_graph:
         try:
             static_ids = ids_dev.clone()
@@ -298,7 +298,7 @@ def run_ours(args, cfg, layers):
     # (both fused entry points are wrapped at the binding level, so module calls and the producer-fused
     # path are covered alike)
     lin_time, lin_ops, n_lin = 0.0, 0.0, 0
-    if args.parallel == "dp" or world == 1:
+    if True:
         events = []
         originals = {name: getattr(_lib, name) for name in ("w8a8_linear", "w8a8_linear_q8", "fp8_linear")}
 
@@ -387,9 +387,16 @@ def run_ours(args, cfg, layers):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, S, layers)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # release the captured graph (it may hold NCCL work) before tearing the communicator down, and never
+        # let a slow communicator shutdown hold the box: the result line is already printed
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

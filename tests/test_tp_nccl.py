@@ -1,0 +1,70 @@
+"""Tensor-parallel path on real GPUs (needs >= 2 CUDA devices; skipped on the single-GPU test box).
+
+world_size 2 over NCCL: the row-parallel int32 mode must reproduce the unsharded module bit for bit
+(per-tensor and per-token, the latter through the max-all-reduced row scales), and the tensor-parallel
+decoder stack must agree with the single-GPU stack up to the bf16 rounding of the partial sums.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from autosmoothquant_b200 import harness, tp
+        from autosmoothquant_b200.layers.nn.linear import W8A8BFP32OFP32LinearWithQuantScale
+
+        torch.manual_seed(0)
+        K, N = 1024, 768
+        lin = torch.nn.Linear(K, N, bias=True)
+        x = torch.randn(300, K).to(torch.bfloat16).to(dev)
+        results = {}
+        for act in ("per-tensor", "per-token"):
+            full = W8A8BFP32OFP32LinearWithQuantScale.from_float(lin, 0.05, act_quant=act).to(dev)
+            want = full(x)
+            row = tp.RowParallelLinear(tp.shard_row(full, rank, world).to(dev), reduce="int32", has_bias=True)
+            lo, hi = rank * K // world, (rank + 1) * K // world
+            got = row(x[:, lo:hi].contiguous())
+            results[f"int32 {act}"] = bool(torch.equal(got, want))
+            row_n = tp.RowParallelLinear(tp.shard_row(full, rank, world).to(dev), reduce="native", has_bias=True)
+            got_n = row_n(x[:, lo:hi].contiguous())
+            results[f"native {act}"] = bool(torch.allclose(got_n.float(), want.float(), rtol=2 ** -6, atol=2 ** -6 * float(want.abs().max())))
+        # decoder stack: TP (fused + producer kernels) vs single GPU
+        ids = torch.randint(0, harness.TINY.vocab, (2, 64), generator=torch.Generator().manual_seed(0)).to(dev)
+        ref = harness.QuantDecoder(harness.TINY, {}, device=dev, seed=3, fuse_projections=True, glue=True)(ids, last_token_only=False)
+        for glue in (True, False):
+            model = tp.build_tp_decoder(harness.TINY, layers=None, device=dev, world=world, rank=rank, seed=3, glue=glue)
+            out = model(ids, last_token_only=False)
+            results[f"decoder glue={glue}"] = bool(float((out - ref).abs().max()) <= 0.08 * float(ref.abs().max()))
+        ret[rank] = results
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp2_nccl_matches_single_gpu():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        for name, ok in ret[rank].items():
+            assert ok, f"rank {rank}: {name}"
