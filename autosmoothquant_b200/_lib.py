@@ -106,13 +106,13 @@ def load():
         lib.asq_fp8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f, c_f,
                                        c_vp, c_i, c_vp, c_sz, c_vp]
         lib.asq_i8gemm_o32.restype = c_i
-        lib.asq_i8gemm_o32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]
+        lib.asq_i8gemm_o32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_sz, c_vp]
         lib.asq_i8gemm_epi.restype = c_i
-        lib.asq_i8gemm_epi.argtypes = [c_vp, c_vp, c_vp, c_i, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_f, c_i, c_vp]
+        lib.asq_i8gemm_epi.argtypes = [c_vp, c_vp, c_vp, c_i, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_f, c_i, c_vp, c_sz, c_vp]
         lib.asq_quantize_act.restype = c_i
         lib.asq_quantize_act.argtypes = [c_vp, c_i, c_vp, c_vp, c_i64, c_i64, c_i, c_f, c_i, c_i, c_vp]
         lib.asq_w8a8_linear_q8.restype = c_i
-        lib.asq_w8a8_linear_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp, c_vp]
+        lib.asq_w8a8_linear_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp, c_vp, c_sz, c_vp]
         lib.asq_add_rmsnorm_quant.restype = c_i
         lib.asq_add_rmsnorm_quant.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_f, c_vp]
         lib.asq_silu_mul_quant.restype = c_i
@@ -175,7 +175,7 @@ def _workspace(dev: torch.device, stream: int, nbytes: int) -> Tuple[int, int]:
     with _ws_lock:
         buf = _ws_cache.get(key)
         if buf is None or buf.numel() < nbytes + 1024:
-            size = max(nbytes + 1024, 1 << 20)
+            size = max(nbytes + 1024, 1 << 25)
             size = 1 << (size - 1).bit_length()  # grow geometrically
             buf = torch.zeros(size, dtype=torch.uint8, device=dev)
             _ws_cache[key] = buf
@@ -294,9 +294,12 @@ def i8gemm_o32(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> None:
         raise ValueError("i8gemm_o32 expects contiguous tensors")
     if a.shape[0] == 0:
         return
+    lib = load()
     with torch.cuda.device(dev):
-        rc = load().asq_i8gemm_o32(a.data_ptr(), w.data_ptr(), out.data_ptr(), a.shape[0], w.shape[0], a.shape[1],
-                                   _stream(dev))
+        stream = _stream(dev)
+        ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(0, 0))
+        rc = lib.asq_i8gemm_o32(a.data_ptr(), w.data_ptr(), out.data_ptr(), a.shape[0], w.shape[0], a.shape[1],
+                                ws, ws_bytes, stream)
     _check(rc)
     _launches += 1
 
@@ -323,11 +326,14 @@ def i8gemm_epi(
         raise ValueError("bias must be a contiguous [N] tensor")
     if a.shape[0] == 0:
         return
+    lib = load()
     with torch.cuda.device(dev):
-        rc = load().asq_i8gemm_epi(
+        stream = _stream(dev)
+        ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(0, 0))
+        rc = lib.asq_i8gemm_epi(
             a.data_ptr(), w.data_ptr(), _ptr(bias), _code(bias.dtype) if bias is not None else ASQ_F32,
             out.data_ptr(), _code(out.dtype), a.shape[0], w.shape[0], a.shape[1], float(alpha), float(beta),
-            EPI_RELU if relu else 0, _stream(dev),
+            EPI_RELU if relu else 0, ws, ws_bytes, stream,
         )
     _check(rc)
     _launches += 1
@@ -391,9 +397,12 @@ def w8a8_linear_q8(
     y = torch.empty((M, N), dtype=out_dtype, device=dev)
     if M == 0:
         return y
+    lib = load()
     with torch.cuda.device(dev):
-        rc = load().asq_w8a8_linear_q8(xq.data_ptr(), _ptr(row_scale), weight.data_ptr(), _ptr(bias), y.data_ptr(),
-                                       _code(out_dtype), M, N, K, float(dequant_scale), _ptr(col_scale), _stream(dev))
+        stream = _stream(dev)
+        ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(0, 0))
+        rc = lib.asq_w8a8_linear_q8(xq.data_ptr(), _ptr(row_scale), weight.data_ptr(), _ptr(bias), y.data_ptr(),
+                                    _code(out_dtype), M, N, K, float(dequant_scale), _ptr(col_scale), ws, ws_bytes, stream)
     _check(rc)
     _launches += 1
     return y

@@ -76,7 +76,13 @@ struct LinearParams {
   int M, N, K;
   int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
   int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;  // num_n_blocks = TILE_N-wide tiles per row
-  int n_units, rounds, tail_tiles, tail_q;                        // balanced schedule (see TileWalk)
+  int n_units, tile_units, rounds, tail_tiles;                    // schedule (see TileWalk)
+  // stream-K tail: the k-iterations of the left-over tiles are dealt evenly to all workers; partial
+  // accumulators travel through `sk_partial` (one 128-row x 256-column fp32/int32 slot per CTA), handshake
+  // words in `sk_flags` (one per epilogue warp, set by the contributor, cleared by the owner)
+  int sk_enabled, sk_total, sk_workers;  // sk_workers <= launched workers: every participant gets >= 1 iteration
+  uint32_t* sk_partial;
+  uint32_t* sk_flags;
   int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
   unsigned long long* dbg;  // optional timeline buffer (8 slots per CTA), nullptr in production
 };
@@ -561,42 +567,84 @@ struct TileCfg {
 };
 
 // The sequence of tiles one worker (CTA or CTA pair) processes; every warp role walks it identically.
-//   rounds x  full tiles  t = round * W + worker            (round-robin, TILE_N wide)
-//   then      the R = T - rounds * W left-over tiles are cut into 64-column units and dealt `tail_q` units
-//             per worker, so the last round costs tail_q/4 of a tile instead of a whole one.
+//   rounds x  full tiles  t = round * W + worker   (round-robin)
+//   then      the R = T - rounds * W left-over tiles: one per worker, or — stream-K — their k-iterations dealt
+//             evenly to the workers, every tile finished by the worker that holds its first k-block (the
+//             "owner", which adds the other workers' partial accumulators before its epilogue).
+struct Seg {
+  int m_blk, col0, width;  // output tile
+  int kb0, kb1;            // k-block range [kb0, kb1) this worker accumulates
+  int role;                // SEG_COMPLETE: whole K, normal epilogue; SEG_CONTRIB: writes a partial; SEG_OWNER: adds partials
+  int tile_g0;             // owner: first stream-K iteration index of its tile
+};
+enum : int { SEG_COMPLETE = 0, SEG_CONTRIB = 1, SEG_OWNER = 2 };
+
 struct TileWalk {
   const LinearParams& p;
   int worker, W, round, g, g_end;
-  __device__ TileWalk(const LinearParams& p_, int worker_, int W_) : p(p_), worker(worker_), W(W_), round(0) {
-    g = worker_ * p_.tail_q;
-    g_end = min(g + p_.tail_q, p_.tail_tiles * (TILE_N / UNIT_N));
+  __device__ static long long sk_begin(const LinearParams& p, int w) {
+    return static_cast<long long>(w) * p.sk_total / p.sk_workers;
   }
-  __device__ bool next(int& m_blk, int& col0, int& width) {
-    constexpr int U = TILE_N / UNIT_N;
+  __device__ TileWalk(const LinearParams& p_, int worker_, int W_) : p(p_), worker(worker_), W(W_), round(0), g(0), g_end(0) {
+    if (p_.sk_enabled && worker_ < p_.sk_workers) {
+      g = static_cast<int>(sk_begin(p_, worker_));
+      g_end = static_cast<int>(sk_begin(p_, worker_ + 1));
+    } else if (!p_.sk_enabled && worker_ < p_.tail_tiles) {
+      g = worker_;  // plain tail: one left-over tile per worker
+      g_end = worker_ + 1;
+    }
+  }
+  __device__ void set_tile(Seg& sg, int t) const {
     int n_blk;
+    tile_coords(t, p, sg.m_blk, n_blk);
+    const int U = p.tile_units;  // tile width in 64-column units: 4, or fewer for decode-sized problems
+    sg.col0 = n_blk * U * UNIT_N;
+    sg.width = min(U, p.n_units - n_blk * U) * UNIT_N;
+  }
+  __device__ bool next(Seg& sg) {
+    sg.kb0 = 0;
+    sg.kb1 = p.num_k_blocks;
+    sg.role = SEG_COMPLETE;
+    sg.tile_g0 = 0;
     if (round < p.rounds) {
-      tile_coords(round * W + worker, p, m_blk, n_blk);
+      set_tile(sg, round * W + worker);
       ++round;
-      col0 = n_blk * TILE_N;
-      width = min(U, p.n_units - n_blk * U) * UNIT_N;
       return true;
     }
-    while (g < g_end) {
-      const int j = g / U, k = g % U;
-      tile_coords(p.rounds * W + j, p, m_blk, n_blk);
-      const int nu = n_blk * U + k;
-      const int avail = min(U - k, g_end - g);
-      g += avail;
-      const int wu = min(avail, p.n_units - nu);
-      if (wu > 0) {
-        col0 = nu * UNIT_N;
-        width = wu * UNIT_N;
-        return true;
-      }
+    if (g >= g_end) return false;
+    if (!p.sk_enabled) {
+      set_tile(sg, p.rounds * W + g);
+      ++g;
+      return true;
     }
-    return false;
+    // stream-K: this worker's share [g, g_end) of the tail's k-iterations, cut at tile boundaries
+    const int nkb = p.num_k_blocks;
+    const int j = g / nkb;
+    sg.kb0 = g - j * nkb;
+    sg.kb1 = min(nkb, sg.kb0 + (g_end - g));
+    sg.tile_g0 = j * nkb;
+    g += sg.kb1 - sg.kb0;
+    set_tile(sg, p.rounds * W + j);
+    if (sg.kb0 == 0) sg.role = (sg.kb1 == nkb) ? SEG_COMPLETE : SEG_OWNER;
+    else sg.role = SEG_CONTRIB;
+    return true;
   }
 };
+
+// Stream-K scratch addressing.  Slot = one CTA's 128 x 256 accumulator of a contributor; inside a slot every
+// epilogue warp owns 16 KB laid out [chunk(4)][16-byte quad(8)][lane(32)] so that both the contributor's
+// stores and the owner's loads are fully coalesced 512-byte warp accesses.
+constexpr uint32_t SK_WARP_WORDS = 4 * 8 * 32 * 4;                  // 4096 words = 16 KB per warp
+constexpr uint32_t SK_SLOT_WORDS = NUM_EPI_WARPS * SK_WARP_WORDS;   // 128 KB per CTA
+__device__ __forceinline__ uint32_t* sk_warp_base(const LinearParams& p, int contributor, int cg, uint32_t cta_rank, int ew) {
+  return p.sk_partial + (static_cast<size_t>(contributor) * cg + cta_rank) * SK_SLOT_WORDS + ew * SK_WARP_WORDS;
+}
+__device__ __forceinline__ uint32_t* sk_flag(const LinearParams& p, int contributor, int cg, uint32_t cta_rank, int ew) {
+  return p.sk_flags + (static_cast<size_t>(contributor) * cg + cta_rank) * NUM_EPI_WARPS + ew;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ------------------------------------------------------------------ the kernel
 template <bool FP8, int CG>
@@ -660,14 +708,15 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       bool first = true;
       TileWalk walk(p, worker, num_workers);
-      int m_blk, col0, width;
-      while (walk.next(m_blk, col0, width)) {
+      Seg sg;
+      while (walk.next(sg)) {
+        const int m_blk = sg.m_blk, col0 = sg.col0, width = sg.width;
         const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's A rows
         const int b_rows = width / CG;                                                  // this CTA's W rows
         const int w_row = col0 + static_cast<int>(cta_rank) * b_rows;
         const uint32_t stage_tx = CG * (Cfg::A_BYTES + static_cast<uint32_t>(b_rows) * BLOCK_K);
         bool panel_ready = !fused || row0 >= p.M;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), stage_tx);
           const uint32_t sA = base + stage * Cfg::A_BYTES;
@@ -707,25 +756,25 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int it = 0;
       TileWalk walk(p, worker, num_workers);
-      int m_blk, col0, width;
-      for (; walk.next(m_blk, col0, width); ++it) {
-        const uint32_t idesc = idesc_base | (static_cast<uint32_t>(width >> 3) << 17);
+      Seg sg;
+      for (; walk.next(sg); ++it) {
+        const uint32_t idesc = idesc_base | (static_cast<uint32_t>(sg.width >> 3) << 17);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogues (both CTAs) drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TILE_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (it == 0 && kb == 0) ASQ_STAMP(4);
+          if (it == 0 && kb == sg.kb0) ASQ_STAMP(4);
           const uint64_t adesc = make_smem_desc_sw128(base + stage * Cfg::A_BYTES);
           const uint64_t bdesc = make_smem_desc_sw128(base + STAGES * Cfg::A_BYTES + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             const uint64_t koff = static_cast<uint64_t>(k * (UMMA_K >> 4));
-            const uint32_t accum = (kb | k) != 0;
+            const uint32_t accum = (kb != sg.kb0) || (k != 0);
             if (CG == 2) {
               if (FP8) mma_f8_pair(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
               else     mma_i8_pair(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
@@ -776,8 +825,9 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     int it = 0;
     TileWalk walk(p, worker, num_workers);
-    int m_blk, tile_col0, width;
-    for (; walk.next(m_blk, tile_col0, width); ++it) {
+    Seg sg;
+    for (; walk.next(sg); ++it) {
+      const int m_blk = sg.m_blk, tile_col0 = sg.col0, width = sg.width;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quad * 32;
@@ -785,17 +835,65 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
       const int ngroups = width / UNIT_N;
       float rs = 0.f;
+      // stream-K owner: the workers after this one hold the rest of this tile's K range
+      int n_contrib = 0;
+      if (sg.role == SEG_OWNER) {
+        const long long tile_end = static_cast<long long>(sg.tile_g0) + p.num_k_blocks;
+        for (int c = worker + 1; c < p.sk_workers && TileWalk::sk_begin(p, c) < tile_end; ++c) ++n_contrib;
+        if (lane == 0) {
+          for (int c = 0; c < n_contrib; ++c) {
+            const uint32_t* f = sk_flag(p, worker + 1 + c, CG, cta_rank, ew);
+            while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (it == 0 && ew == 0 && lane == 0) ASQ_STAMP(5);
       if (per_token_epi && row < p.M) rs = __ldcg(p.row_scale + row);
+      int chunk_pair = 0;  // index of the (r0, r1) pair inside this warp's stream-K region
 #pragma unroll 1
-      for (int g = half; g < ngroups; g += 2) {
+      for (int g = half; g < ngroups; g += 2, ++chunk_pair) {
         const uint32_t taddr = taddr0 + g * UNIT_N;
         const int col0 = tile_col0 + g * UNIT_N;
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(taddr, r0);
         tmem_ld_32x32(taddr + 32, r1);
+        if (sg.role == SEG_CONTRIB) {
+          // raw partial accumulators -> scratch, coalesced: uint4 index (chunk*8 + quad16)*32 + lane
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(sk_warp_base(p, worker, CG, cta_rank, ew)) + chunk_pair * 2 * 8 * 32 + lane;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) __stcg(dst + q * 32, make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) __stcg(dst + (8 + q) * 32, make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]));
+          continue;
+        }
+        if (sg.role == SEG_OWNER) {
+          tmem_ld_wait();
+          for (int c = 0; c < n_contrib; ++c) {
+            const uint4* src = reinterpret_cast<const uint4*>(sk_warp_base(p, worker + 1 + c, CG, cta_rank, ew)) + chunk_pair * 2 * 8 * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 a = __ldcg(src + q * 32);
+              const uint4 b = __ldcg(src + (8 + q) * 32);
+              if (FP8) {
+                r0[4 * q] = __float_as_uint(__uint_as_float(r0[4 * q]) + __uint_as_float(a.x));
+                r0[4 * q + 1] = __float_as_uint(__uint_as_float(r0[4 * q + 1]) + __uint_as_float(a.y));
+                r0[4 * q + 2] = __float_as_uint(__uint_as_float(r0[4 * q + 2]) + __uint_as_float(a.z));
+                r0[4 * q + 3] = __float_as_uint(__uint_as_float(r0[4 * q + 3]) + __uint_as_float(a.w));
+                r1[4 * q] = __float_as_uint(__uint_as_float(r1[4 * q]) + __uint_as_float(b.x));
+                r1[4 * q + 1] = __float_as_uint(__uint_as_float(r1[4 * q + 1]) + __uint_as_float(b.y));
+                r1[4 * q + 2] = __float_as_uint(__uint_as_float(r1[4 * q + 2]) + __uint_as_float(b.z));
+                r1[4 * q + 3] = __float_as_uint(__uint_as_float(r1[4 * q + 3]) + __uint_as_float(b.w));
+              } else {  // int32 partial sums: exact and order-independent
+                r0[4 * q] += a.x; r0[4 * q + 1] += a.y; r0[4 * q + 2] += a.z; r0[4 * q + 3] += a.w;
+                r1[4 * q] += b.x; r1[4 * q + 1] += b.y; r1[4 * q + 2] += b.z; r1[4 * q + 3] += b.w;
+              }
+            }
+          }
+        }
         if (staged && out16) {
           // 64 output columns (two TMEM chunks) fill one 128-byte wide staging tile
           const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
@@ -860,6 +958,9 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
         else         mbar_arrive(tempty_bar(acc));
+        if (sg.role == SEG_CONTRIB) st_release_gpu(sk_flag(p, worker, CG, cta_rank, ew), 1u);  // partial published
+        if (sg.role == SEG_OWNER)
+          for (int c = 0; c < n_contrib; ++c) *sk_flag(p, worker + 1 + c, CG, cta_rank, ew) = 0u;  // consumed: re-arm
       }
     }
     if (lane == 0) tma_store_wait_all();  // staged tiles fully written before the CTA retires
@@ -993,20 +1094,29 @@ struct Workspace {
   uint8_t* a_q;
   float* row_scale;
   uint32_t* sync;
+  uint32_t* sk_flags;
+  uint32_t* sk_partial;
 };
-// Layout: [phase counters: fixed kSyncBytes] [row scales: M fp32] [8-bit copy of x: M*K].  The counters
-// sit at a fixed offset so a cached, zero-initialised buffer stays valid when M and K change.
-constexpr size_t kSyncBytes = 32768;  // 8192 counters -> up to 8191 panels (about 1M rows)
+// Layout: [phase counters: kSyncBytes] [stream-K handshake words: kSkFlagBytes] [stream-K partial accumulators:
+// kSkPartialBytes] [row scales: M fp32] [8-bit copy of x: M*K].  Everything the kernels expect to find zeroed
+// sits at fixed offsets, so a cached, zero-initialised buffer stays valid when M and K change.
+constexpr size_t kSyncBytes = 32768;  // 8192 counters -> up to 8189 panels (about 1M rows)
+constexpr int kSkMaxCtas = 160;       // >= SM count of any sm_100 part
+constexpr size_t kSkFlagBytes = 8192; // kSkMaxCtas * 8 warps * 4 bytes, rounded up
+constexpr size_t kSkPartialBytes = static_cast<size_t>(kSkMaxCtas) * asq::SK_SLOT_WORDS * 4;  // 20 MB
+constexpr size_t kFixedBytes = kSyncBytes + kSkFlagBytes + kSkPartialBytes;
 size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
   const size_t rs = round_up(static_cast<size_t>(M) * 4, 1024);
   const size_t aq = round_up(static_cast<size_t>(M) * K, 1024);
   if (w != nullptr) {
     uint8_t* b = static_cast<uint8_t*>(base);
     w->sync = reinterpret_cast<uint32_t*>(b);
-    w->row_scale = reinterpret_cast<float*>(b + kSyncBytes);
-    w->a_q = b + kSyncBytes + rs;
+    w->sk_flags = reinterpret_cast<uint32_t*>(b + kSyncBytes);
+    w->sk_partial = reinterpret_cast<uint32_t*>(b + kSyncBytes + kSkFlagBytes);
+    w->row_scale = reinterpret_cast<float*>(b + kFixedBytes);
+    w->a_q = b + kFixedBytes + rs;
   }
-  return kSyncBytes + rs + aq;
+  return kFixedBytes + rs + aq;
 }
 
 template <bool FP8, int CG>
@@ -1014,8 +1124,17 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
                const asq::LinearParams& p, int workers, cudaStream_t stream) {
   using Cfg = asq::TileCfg<CG>;
   auto kern = asq::asq_linear_kernel<FP8, CG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  cudaError_t e;
+  {
+    static bool attr_set[kMaxDevices] = {};  // per template instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set[dev] = true;
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(workers * CG), 1, 1);
@@ -1046,6 +1165,18 @@ int pick_cta_group(int64_t M) {
   return M > asq::BLOCK_M ? 2 : 1;
 }
 
+// Optional workspace of the GEMM-only entry points: only the stream-K region is used.
+int attach_streamk(asq::LinearParams& p, void* workspace, size_t workspace_bytes) {
+  if (workspace == nullptr) return ASQ_OK;  // no workspace: no stream-K split, everything else works
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(ASQ_ERR_INVALID, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < kFixedBytes) return fail(ASQ_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", kFixedBytes, workspace_bytes);
+  Workspace ws;
+  ws_layout(0, 16, workspace, &ws);
+  p.sk_flags = ws.sk_flags;
+  p.sk_partial = ws.sk_partial;
+  return ASQ_OK;
+}
+
 // Shared launcher: `a8` is the 8-bit A matrix TMA reads (caller's matrix, or the workspace copy).
 int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p, cudaStream_t stream) {
   int dev;
@@ -1060,11 +1191,20 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   }
   const int cg = pick_cta_group(p.M);
   const int tile_m = asq::BLOCK_M * cg;
-  constexpr int U = asq::TILE_N / asq::UNIT_N;
+  const int max_workers = st->sm_count / cg;
   p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
   p.n_units = (p.N + asq::UNIT_N - 1) / asq::UNIT_N;
-  p.num_n_blocks = (p.n_units + U - 1) / U;
   p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
+  // Tile width in 64-column units.  Narrower tiles for decode-sized problems were measured slower on B200
+  // (profiles/r01_notes.md: with 8-16 KB W boxes the 3-5 stage ring keeps too few bytes in flight), so the
+  // width stays 256; ASQ_TILE_UNITS=1|2 narrows it for experiments.
+  p.tile_units = asq::TILE_N / asq::UNIT_N;
+  {
+    static int tu_env = -1;
+    if (tu_env < 0) { const char* e = getenv("ASQ_TILE_UNITS"); tu_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
+    if (tu_env) p.tile_units = tu_env;
+  }
+  p.num_n_blocks = (p.n_units + p.tile_units - 1) / p.tile_units;
   {
     // ASQ_RASTER=n<G> | m<G> overrides the walk (experiments)
     static int raster_env = -1, group_env = 0;
@@ -1074,30 +1214,47 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (e != nullptr && e[0] == 'm') { raster_env = 1; group_env = atoi(e + 1); }
       else if (e != nullptr && e[0] == 'n') { raster_env = 2; group_env = atoi(e + 1); }
     }
-    // default: keep one group's W tiles (group * 256 * K bytes) within ~48 MB of the 126 MB L2
-    const long long per_block = static_cast<long long>(asq::TILE_N) * p.K;
+    // default: keep one group's W tiles (group * width * K bytes) within ~48 MB of the 126 MB L2
+    const long long per_block = static_cast<long long>(p.tile_units) * asq::UNIT_N * p.K;
     long long gn = (48ll << 20) / per_block;
     p.raster_m = 0;
     p.group = static_cast<int>(gn < 1 ? 1 : (gn > p.num_n_blocks ? p.num_n_blocks : gn));
     if (raster_env == 1) { p.raster_m = 1; p.group = group_env > 0 ? group_env : p.num_m_blocks; }
     if (raster_env == 2 && group_env > 0) p.group = group_env;
   }
-  // Balanced schedule: `rounds` full tiles per worker, then the left-over tiles dealt in 64-column units.
+  // `rounds` full tiles per worker, then the left-over tiles: one each, or split along K (stream-K)
   const long long tiles = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
-  const int max_workers = st->sm_count / cg;
-  // Measured on B200 (profiles/r01_notes.md): narrow tail tiles are L2-feed bound (a 256x64 pair tile moves
-  // 20 KB per 128 MMA cycles), so dealing the last round in 64-column units is slower than one more round
-  // of full tiles; the split stays available for experiments (ASQ_TAIL_SPLIT=1).
-  static int no_split = -1;
-  if (no_split < 0) { const char* e = getenv("ASQ_TAIL_SPLIT"); no_split = !(e != nullptr && e[0] == '1'); }
-  int workers = max_workers;
   p.rounds = static_cast<int>(tiles / max_workers);
   p.tail_tiles = static_cast<int>(tiles - static_cast<long long>(p.rounds) * max_workers);
-  if (p.tail_tiles > 0) {
-    p.tail_q = no_split ? U : (p.tail_tiles * U + max_workers - 1) / max_workers;
-    if (p.rounds == 0) workers = (p.tail_tiles * U + p.tail_q - 1) / p.tail_q;
-  } else {
-    p.tail_q = 0;
+  int workers = p.rounds > 0 ? max_workers : p.tail_tiles;
+
+  // Stream-K tail: instead of one more (mostly idle) round, the left-over tiles' k-iterations are dealt evenly
+  // to the workers; also spreads problems with fewer tiles than SMs (decode-sized M) over the whole chip.
+  p.sk_enabled = 0;
+  {
+    int sk_env_effective = 1;
+    // Measured (profiles/r01_notes.md): with >= 1 full round the fix-up (contributor store -> owner load ->
+    // epilogue, ~4 us on the critical path) costs more than the saved fraction of a round at K <= 11008, and
+    // with many contributors per tile the owner's serial additions dominate; by default the split is used
+    // only when there are fewer tiles than workers AND K is long (>= 64 k-blocks), at most 4-way.
+    // ASQ_STREAMK=0 disables it, ASQ_STREAMK=2 forces it for every tail.
+    static int sk_env = -1;
+    if (sk_env < 0) { const char* e = getenv("ASQ_STREAMK"); sk_env = (e == nullptr) ? 1 : (e[0] - '0'); }
+    if (sk_env == 1 && (p.rounds > 0 || p.num_k_blocks < 64)) sk_env_effective = 0;  // decode-sized M with a long K only
+    constexpr int kMinIters = 4;  // k-blocks per stream-K segment, bounds the fix-up overhead
+    const long long total_it = static_cast<long long>(p.tail_tiles) * p.num_k_blocks;
+    if (sk_env_effective && sk_env && p.tail_tiles > 0 && p.tail_tiles < max_workers && total_it / kMinIters >= 2 && total_it < (1ll << 30)) {
+      if (p.sk_partial != nullptr && p.sk_flags != nullptr && max_workers * cg <= kSkMaxCtas) {  // caller gave a workspace
+        long long sw = total_it / kMinIters;
+        if (sk_env == 1 && sw > 4ll * p.tail_tiles) sw = 4ll * p.tail_tiles;  // the owner adds its contributors serially
+        p.sk_workers = static_cast<int>(sw < max_workers ? sw : max_workers);
+        if (p.sk_workers > p.tail_tiles) {  // otherwise whole tiles per worker are just as good
+          p.sk_enabled = 1;
+          p.sk_total = static_cast<int>(total_it);
+          workers = p.rounds > 0 ? max_workers : p.sk_workers;
+        }
+      }
+    }
   }
 
   CUtensorMap tmA, tmB, tmBu;
@@ -1171,6 +1328,7 @@ int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const floa
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.sync = ws.sync;
+  p.sk_flags = ws.sk_flags; p.sk_partial = ws.sk_partial;
   if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN) p.row_scale_in = row_scale_out;  // in: caller-supplied scales
   else p.row_scale_out = row_scale_out;
   p.quant_scale = quant_scale; p.inv_quant_scale = 1.0f / quant_scale;
@@ -1200,7 +1358,7 @@ int asq_device_supported(void) {
 }
 
 size_t asq_workspace_bytes(int64_t M, int64_t K) {
-  if (M <= 0 || K <= 0) return 1024;
+  if (M <= 0 || K <= 0) return kFixedBytes;  // GEMM-only entry points: counters + stream-K region
   return ws_layout(M, K, nullptr, nullptr);
 }
 
@@ -1223,12 +1381,14 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
 
 int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,
                        int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
-                       void* stream) {
+                       void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(xq, w, y, M, N, K);
   if (rc != ASQ_OK || M == 0) return rc;
   if (!is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "y dtype must be f32, f16 or bf16");
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
+  rc = attach_streamk(p, workspace, workspace_bytes);
+  if (rc != ASQ_OK) return rc;
   p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT;
@@ -1238,18 +1398,22 @@ int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w
   return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream));
 }
 
-int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c, int64_t M, int64_t N, int64_t K, void* stream) {
+int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c, int64_t M, int64_t N, int64_t K,
+                   void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(a, w, c, M, N, K);
   if (rc != ASQ_OK || M == 0) return rc;
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
+  rc = attach_streamk(p, workspace, workspace_bytes);
+  if (rc != ASQ_OK) return rc;
   p.y = c; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.y_dtype = ASQ_I32; p.epi_kind = asq::EPI_RAW_I32; p.act_mode = ASQ_ACT_ROUND;
   return launch_linear(false, a, w, p, static_cast<cudaStream_t>(stream));
 }
 
 int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_dtype, void* y, int y_dtype,
-                   int64_t M, int64_t N, int64_t K, float alpha, float beta, int flags, void* stream) {
+                   int64_t M, int64_t N, int64_t K, float alpha, float beta, int flags,
+                   void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(a, w, y, M, N, K);
   if (rc != ASQ_OK || M == 0) return rc;
   if (y_dtype != ASQ_I8 && y_dtype != ASQ_I32 && !is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "bad y_dtype %d", y_dtype);
@@ -1260,6 +1424,8 @@ int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_
   p.y = y; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.y_dtype = y_dtype; p.epi_kind = asq::EPI_ALPHA_BETA; p.act_mode = ASQ_ACT_ROUND;
   p.alpha = alpha; p.beta = beta; p.bias_any = bias; p.bias_dtype = bias_dtype; p.flags = flags;
+  rc = attach_streamk(p, workspace, workspace_bytes);
+  if (rc != ASQ_OK) return rc;
   return launch_linear(false, a, w, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -96,11 +96,13 @@ const char* asq_last_error(void);
 /* 1 if the current CUDA device can run the kernels (compute capability 10.0), else 0. */
 int asq_device_supported(void);
 
-/* Bytes of scratch the fused entry points need for an [M,K] activation:
- * the int8/e4m3 copy of x, M fp32 row scales and the phase counters.  The
- * buffer must be 1024-byte aligned device memory, zero-filled once when
- * allocated (the kernels restore the counters to zero before they exit), and
- * must not be shared by calls that may run concurrently. */
+/* Bytes of scratch for an [M,K] activation: the phase counters, the stream-K
+ * region (handshake words + partial accumulators, ~20 MB), M fp32 row scales and
+ * the int8/e4m3 copy of x.  asq_workspace_bytes(0, 0) is what the GEMM-only entry
+ * points can use (their workspace is optional: without it decode-sized problems
+ * are not split along K).  The buffer must be 1024-byte aligned device memory,
+ * zero-filled once when allocated (the kernels leave every word they rely on at
+ * zero again), and must not be shared by calls that may run concurrently. */
 size_t asq_workspace_bytes(int64_t M, int64_t K);
 
 /* y = dequant( quant(x) . w^T ) [+ bias], one launch.
@@ -143,12 +145,14 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
  * per-token scales for the epilogue. */
 int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
                        void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                       float dequant_scale, const float* col_scale, void* stream);
+                       float dequant_scale, const float* col_scale,
+                       void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
 /* c[M,N] (int32) = a[M,K] (int8) . w[N,K]^T (int8), exact.  Drop-in for
  * I8CUGEMM::linear_a8_w8_o32_ and the exactness tap of the fused kernels. */
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c,
-                   int64_t M, int64_t N, int64_t K, void* stream);
+                   int64_t M, int64_t N, int64_t K,
+                   void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
 /* INT8-in GEMM with a scaling epilogue (the o8 methods of I8CUGEMM and the
  * csrc/kernels/linear.cu variants):
@@ -156,7 +160,8 @@ int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c,
  *   y = y_dtype == I8 ? sat_i8(rint(v)) : y_dtype == I32 ? rint(v) : v     (ReLU first if flagged) */
 int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_dtype,
                    void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                   float alpha, float beta, int flags, void* stream);
+                   float alpha, float beta, int flags, 
+                   void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
 /* Debug / parity tap of the fused prologue: writes the quantised activations
  * (int8, or e4m3 bytes when fp8 != 0) and, for per-token, the row scales. */
