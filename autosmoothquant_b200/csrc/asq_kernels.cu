@@ -647,7 +647,11 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <bool FP8, int CG>
+// MC = CTA pairs per cluster (1 or 2).  With MC == 2 a cluster of four CTAs owns a 256-row x 512-column
+// super tile: pair p computes columns [p*256, p*256+256), both pairs need the same activation rows, so every
+// CTA fetches only HALF of its 128 A rows and multicasts them to its twin in the other pair.  Per k-block a
+// CTA then pulls 8 KB (A) + 16 KB (W) from L2 instead of 32 KB; the main loop is L2-feed bound.
+template <bool FP8, int CG, int MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmBu, const __grid_constant__ CUtensorMap tmY,
@@ -670,9 +674,12 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
-  const int num_workers = gridDim.x / CG;                        // CTAs (CG=1) or CTA pairs (CG=2)
-  const int worker = blockIdx.x / CG;
+  static_assert(MC == 1 || CG == 2, "multicast clusters are built from CTA pairs");
+  const uint32_t cluster_rank = (CG * MC > 1) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & (CG - 1);              // 0 = leader of the pair
+  const int pair_idx = static_cast<int>(cluster_rank) / CG;       // which pair of the cluster (MC == 2)
+  const int num_workers = gridDim.x / (CG * MC);                  // CTAs, CTA pairs or 4-CTA clusters
+  const int worker = blockIdx.x / (CG * MC);
   const bool fused = (p.x != nullptr);
   if (threadIdx.x == 0) ASQ_STAMP(0);
 
@@ -683,7 +690,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx; TMA bytes of both CTAs land here
-      mbar_init(empty_bar(s), 1);  // one tcgen05.commit (multicast to both CTAs of a pair)
+      mbar_init(empty_bar(s), MC);  // one tcgen05.commit per pair that reads this slot (multicast to its CTAs)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -696,7 +703,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     else         { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();  // peer barriers must exist before remote arrives
+  if (CG * MC > 1) cluster_sync_all(); else __syncthreads();  // peer barriers must exist before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) ASQ_STAMP(1);
@@ -710,7 +717,12 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       TileWalk walk(p, worker, num_workers);
       Seg sg;
       while (walk.next(sg)) {
-        const int m_blk = sg.m_blk, col0 = sg.col0, width = sg.width;
+        const int m_blk = sg.m_blk;
+        // MC == 2: the walk hands out 512-wide super tiles, this pair takes its 256-column half (a half that
+        // lies beyond N still runs, on zero-filled W, because its A multicasts feed the other pair)
+        const int col0 = sg.col0 + pair_idx * TILE_N;
+        int width = (MC == 2) ? min(TILE_N / UNIT_N, p.n_units - col0 / UNIT_N) * UNIT_N : sg.width;
+        if (width <= 0) width = UNIT_N;
         const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's A rows
         const int b_rows = width / CG;                                                  // this CTA's W rows
         const int w_row = col0 + static_cast<int>(cta_rank) * b_rows;
@@ -741,8 +753,16 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             panel_ready = true;
             if (first) ASQ_STAMP(3);
           }
-          if (CG == 2) tma_load_2d_pair(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
-          else         tma_load_2d(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
+          if (MC == 2) {
+            // fetch rows [pair_idx*64, +64) of this CTA's 128 and deliver them to both pairs' same-ranked CTAs
+            const uint16_t mask = static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + CG)));
+            tma_load_2d_pair_mcast(sA + pair_idx * (Cfg::A_BYTES / 2), &tmA, full_bar(stage), kb * BLOCK_K,
+                                   row0 + pair_idx * (BLOCK_M / 2), mask);
+          } else if (CG == 2) {
+            tma_load_2d_pair(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
+          } else {
+            tma_load_2d(sA, &tmA, full_bar(stage), kb * BLOCK_K, row0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         first = false;
@@ -758,7 +778,12 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       TileWalk walk(p, worker, num_workers);
       Seg sg;
       for (; walk.next(sg); ++it) {
-        const uint32_t idesc = idesc_base | (static_cast<uint32_t>(sg.width >> 3) << 17);
+        int width = sg.width;
+        if (MC == 2) {
+          width = min(TILE_N / UNIT_N, p.n_units - (sg.col0 + pair_idx * TILE_N) / UNIT_N) * UNIT_N;
+          if (width <= 0) width = UNIT_N;
+        }
+        const uint32_t idesc = idesc_base | (static_cast<uint32_t>(width >> 3) << 17);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogues (both CTAs) drained this accumulator
@@ -783,12 +808,15 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               else     mma_i8(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
             }
           }
-          // smem slot reusable (in both CTAs) once these MMAs retire
-          if (CG == 2) mma_commit_pair(empty_bar(stage), 3); else mma_commit(empty_bar(stage));
+          // smem slot reusable once these MMAs retire: in both CTAs of the pair, and (MC == 2) in the other
+          // pair too, whose multicast loads write into this pair's slot
+          if (CG == 2) mma_commit_pair(empty_bar(stage), static_cast<uint16_t>((1u << (CG * MC)) - 1u));
+          else         mma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        // accumulator complete -> epilogue warps of both CTAs
-        if (CG == 2) mma_commit_pair(tfull_bar(acc), 3); else mma_commit(tfull_bar(acc));
+        // accumulator complete -> epilogue warps of both CTAs of this pair
+        if (CG == 2) mma_commit_pair(tfull_bar(acc), static_cast<uint16_t>(3u << (pair_idx * CG)));
+        else         mma_commit(tfull_bar(acc));
       }
     }
   } else {
@@ -814,8 +842,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // A tile is width/64 column groups; warps with half == 0 take the even groups, half == 1 the odd ones.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int half = ew >> 2;
-    const uint32_t tempty_leader0 = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
-    const uint32_t tempty_leader1 = (CG == 2) ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
+    const uint32_t tempty_leader0 = (CG == 2) ? mapa_shared(tempty_bar(0), pair_idx * CG) : tempty_bar(0);
+    const uint32_t tempty_leader1 = (CG == 2) ? mapa_shared(tempty_bar(1), pair_idx * CG) : tempty_bar(1);
     const uint32_t stage_base = base + Cfg::EPI_OFFSET + ew * (EPI_BUF_BYTES * EPI_NBUF);
     const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
     const bool staged = p.tma_store != 0;
@@ -827,7 +855,10 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     TileWalk walk(p, worker, num_workers);
     Seg sg;
     for (; walk.next(sg); ++it) {
-      const int m_blk = sg.m_blk, tile_col0 = sg.col0, width = sg.width;
+      const int m_blk = sg.m_blk;
+      const int tile_col0 = sg.col0 + pair_idx * TILE_N;
+      int width = sg.width;
+      if (MC == 2) width = max(0, min(TILE_N / UNIT_N, p.n_units - tile_col0 / UNIT_N)) * UNIT_N;  // 0: nothing to store
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M + quad * 32;
@@ -968,7 +999,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (CG * MC > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -1119,11 +1150,11 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
   return kFixedBytes + rs + aq;
 }
 
-template <bool FP8, int CG>
+template <bool FP8, int CG, int MC>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBu, const CUtensorMap& tmY,
                const asq::LinearParams& p, int workers, cudaStream_t stream) {
   using Cfg = asq::TileCfg<CG>;
-  auto kern = asq::asq_linear_kernel<FP8, CG>;
+  auto kern = asq::asq_linear_kernel<FP8, CG, MC>;
   cudaError_t e;
   {
     static bool attr_set[kMaxDevices] = {};  // per template instantiation, per device
@@ -1137,13 +1168,13 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG), 1, 1);
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG * MC), 1, 1);
   cfg.blockDim = dim3(asq::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG * MC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -1151,6 +1182,38 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBu, tmY, p);
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
+}
+
+// How many 4-CTA clusters of the multicast variant can be co-resident (GPC packing strands a few SMs, e.g.
+// 33 clusters = 132 of 148 SMs); the persistent grid must not exceed it.  Cached per device; 0 = unusable.
+template <bool FP8>
+int max_multicast_clusters(int dev) {
+  static int cached[kMaxDevices];
+  static bool known[kMaxDevices] = {};
+  if (known[dev]) return cached[dev];
+  using Cfg = asq::TileCfg<2>;
+  auto kern = asq::asq_linear_kernel<FP8, 2, 2>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) == cudaSuccess) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(4 * 64, 1, 1);
+    cfg.blockDim = dim3(asq::NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  } else {
+    cudaGetLastError();
+  }
+  cached[dev] = n;
+  known[dev] = true;
+  return n;
 }
 
 // CTA pairs (256-row tiles) whenever there is more than one 128-row panel.  ASQ_FORCE_CG=1|2 overrides
@@ -1191,7 +1254,21 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   }
   const int cg = pick_cta_group(p.M);
   const int tile_m = asq::BLOCK_M * cg;
-  const int max_workers = st->sm_count / cg;
+  int mc_clusters = 0;
+  // 4-CTA multicast clusters (two pairs sharing the activation rows): ASQ_MC=2 enables, =1 disables
+  int mc = 1;
+  {
+    static int mc_env = -1;
+    if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
+    const int want = mc_env ? mc_env : 1;
+    if (want == 2 && cg == 2 && p.N > asq::TILE_N) {
+      const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
+      const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
+      if (clusters > 0 && super_tiles >= clusters) mc = 2;
+      if (mc == 2) mc_clusters = clusters;
+    }
+  }
+  const int max_workers = (mc == 2) ? mc_clusters : st->sm_count / cg;
   p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
   p.n_units = (p.N + asq::UNIT_N - 1) / asq::UNIT_N;
   p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
@@ -1202,7 +1279,24 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   {
     static int tu_env = -1;
     if (tu_env < 0) { const char* e = getenv("ASQ_TILE_UNITS"); tu_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
-    if (tu_env) p.tile_units = tu_env;
+    if (mc == 2) {
+      p.tile_units = 2 * asq::TILE_N / asq::UNIT_N;  // the walk hands out 512-wide super tiles, one half per pair
+    } else if (tu_env) {
+      p.tile_units = tu_env;
+    } else {
+      // Wave quantisation: pick 256- or 192-column tiles, whichever needs less (rounds x width); 192-wide tiles
+      // move ~17% more operand bytes per MAC, charged as a 4% penalty.  E.g. M=2048, N=12288 on 74 CTA pairs:
+      // 384 tiles -> 6 rounds x 256 vs 512 tiles -> 7 rounds x 192 (= 5.25 x 256).
+      auto cost = [&](int units, double penalty) {
+        const long long t = static_cast<long long>(p.num_m_blocks) * ((p.n_units + units - 1) / units);
+        return static_cast<double>((t + max_workers - 1) / max_workers) * units * penalty;
+      };
+      // Measured: a round of 192-wide tiles takes as long as a round of 256-wide ones (the k-block time is set
+      // by operand staging, not by MMA width), so the model below loses in practice; ASQ_TILE_192=1 enables it.
+      static int use192 = -1;
+      if (use192 < 0) { const char* e = getenv("ASQ_TILE_192"); use192 = (e != nullptr && e[0] == '1'); }
+      if (use192 && cost(3, 1.04) < cost(4, 1.0)) p.tile_units = 3;
+    }
   }
   p.num_n_blocks = (p.n_units + p.tile_units - 1) / p.tile_units;
   {
@@ -1243,7 +1337,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (sk_env == 1 && (p.rounds > 0 || p.num_k_blocks < 64)) sk_env_effective = 0;  // decode-sized M with a long K only
     constexpr int kMinIters = 4;  // k-blocks per stream-K segment, bounds the fix-up overhead
     const long long total_it = static_cast<long long>(p.tail_tiles) * p.num_k_blocks;
-    if (sk_env_effective && sk_env && p.tail_tiles > 0 && p.tail_tiles < max_workers && total_it / kMinIters >= 2 && total_it < (1ll << 30)) {
+    if (mc == 1 && sk_env_effective && sk_env && p.tail_tiles > 0 && p.tail_tiles < max_workers && total_it / kMinIters >= 2 && total_it < (1ll << 30)) {
       if (p.sk_partial != nullptr && p.sk_flags != nullptr && max_workers * cg <= kSkMaxCtas) {  // caller gave a workspace
         long long sw = total_it / kMinIters;
         if (sk_env == 1 && sw > 4ll * p.tail_tiles) sw = 4ll * p.tail_tiles;  // the owner adds its contributors serially
@@ -1258,7 +1352,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   }
 
   CUtensorMap tmA, tmB, tmBu;
-  rc = make_tmap(&tmA, a8, p.M, p.K, asq::BLOCK_M);
+  rc = make_tmap(&tmA, a8, p.M, p.K, mc == 2 ? asq::BLOCK_M / 2 : asq::BLOCK_M);
   if (rc != ASQ_OK) return rc;
   rc = make_tmap(&tmB, w, p.N, p.K, asq::TILE_N / cg);
   if (rc != ASQ_OK) return rc;
@@ -1280,10 +1374,12 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       tmY = tmA;  // unused, but must be a valid descriptor
     }
   }
-  if (fp8) return cg == 2 ? launch_cfg<true, 2>(tmA, tmB, tmBu, tmY, p, workers, stream)
-                          : launch_cfg<true, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
-  return cg == 2 ? launch_cfg<false, 2>(tmA, tmB, tmBu, tmY, p, workers, stream)
-                 : launch_cfg<false, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
+  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2>(tmA, tmB, tmBu, tmY, p, workers, stream)
+                          : launch_cfg<false, 2, 2>(tmA, tmB, tmBu, tmY, p, workers, stream);
+  if (fp8) return cg == 2 ? launch_cfg<true, 2, 1>(tmA, tmB, tmBu, tmY, p, workers, stream)
+                          : launch_cfg<true, 1, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
+  return cg == 2 ? launch_cfg<false, 2, 1>(tmA, tmB, tmBu, tmY, p, workers, stream)
+                 : launch_cfg<false, 1, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
 }
 
 int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {

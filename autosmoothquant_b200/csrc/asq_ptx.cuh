@@ -214,6 +214,18 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtens
       ::"r"(dst_smem), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// Pair load that is also multicast to the same-ranked CTA of other pairs of the cluster: the box lands at
+// the same shared-memory offset in every CTA of `cta_mask`, completion bytes are counted on each destination
+// pair's leader barrier.
+__device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t dst_smem, const CUtensorMap* tm, uint32_t bar,
+                                                       int32_t c0, int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst_smem), "l"(tm), "r"(bar & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                : "memory");
