@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = (
     "asq_i8gemm_epi",
     "asq_quantize_act",
     "asq_w8a8_linear_q8",
+    "asq_w8a8_gateup_swiglu_q8",
     "asq_add_rmsnorm_quant",
     "asq_silu_mul_quant",
     "asq_rope_inplace",
@@ -113,6 +114,9 @@ def load():
         lib.asq_quantize_act.argtypes = [c_vp, c_i, c_vp, c_vp, c_i64, c_i64, c_i, c_f, c_i, c_i, c_vp]
         lib.asq_w8a8_linear_q8.restype = c_i
         lib.asq_w8a8_linear_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp, c_vp, c_sz, c_vp]
+        lib.asq_w8a8_gateup_swiglu_q8.restype = c_i
+        lib.asq_w8a8_gateup_swiglu_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i64, c_i64, c_i64, c_f, c_f,
+                                                  c_vp, c_f, c_i, c_vp]
         lib.asq_add_rmsnorm_quant.restype = c_i
         lib.asq_add_rmsnorm_quant.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_f, c_vp]
         lib.asq_silu_mul_quant.restype = c_i
@@ -406,6 +410,56 @@ def w8a8_linear_q8(
     _check(rc)
     _launches += 1
     return y
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """Load-time re-layout for w8a8_gateup_swiglu: blocks of 32 gate rows (or vector entries) alternate with
+    the 32 matching up rows, so one 64-column accumulator group holds both operands of 32 SwiGLU outputs."""
+    if gate.shape != up.shape or gate.shape[0] % 32:
+        raise ValueError("gate / up must have the same shape with a leading dimension that is a multiple of 32")
+    I = gate.shape[0]
+    rest = gate.shape[1:]
+    return torch.stack((gate.reshape(I // 32, 32, *rest), up.reshape(I // 32, 32, *rest)), dim=1).reshape(2 * I, *rest).contiguous()
+
+
+def w8a8_gateup_swiglu(
+    xq: torch.Tensor,
+    weight_il: torch.Tensor,
+    bias_il: Optional[torch.Tensor],
+    dequant_scale: float = 1.0,
+    col_scale_il: Optional[torch.Tensor] = None,
+    row_scale: Optional[torch.Tensor] = None,
+    out_quant_scale: Optional[float] = None,
+    up_dequant_scale: Optional[float] = None,
+    mid_dtype: torch.dtype = torch.bfloat16,
+    div_mode: Optional[int] = None,
+) -> torch.Tensor:
+    """gate|up INT8 GEMM whose epilogue applies SiLU(gate) * up and (out_quant_scale given) the per-tensor
+    quantisation of the next Linear: returns int8 [M, I], or the product in mid_dtype when out_quant_scale is None.
+    weight_il / bias_il / col_scale_il are in interleave_gate_up order; dequant_scale applies to the gate columns,
+    up_dequant_scale (default: the same) to the up columns, col_scale_il overrides both per column."""
+    global _launches
+    dev = _require_cuda(xq, weight_il, bias_il, col_scale_il, row_scale)
+    if xq.dtype != torch.int8 or weight_il.dtype != torch.int8 or xq.dim() != 2 or xq.shape[1] != weight_il.shape[1]:
+        raise ValueError("w8a8_gateup_swiglu expects int8 [M,K] activations and int8 [2I,K] weights")
+    if not (xq.is_contiguous() and weight_il.is_contiguous()):
+        raise ValueError("w8a8_gateup_swiglu expects contiguous tensors")
+    M, K = xq.shape
+    N = weight_il.shape[0]
+    out_dtype = torch.int8 if out_quant_scale is not None else mid_dtype
+    out = torch.empty((M, N // 2), dtype=out_dtype, device=dev)
+    if M == 0:
+        return out
+    with torch.cuda.device(dev):
+        rc = load().asq_w8a8_gateup_swiglu_q8(
+            xq.data_ptr(), _ptr(row_scale), weight_il.data_ptr(), _ptr(bias_il), out.data_ptr(), _code(out_dtype),
+            _code(mid_dtype), M, N, K, float(dequant_scale),
+            float(dequant_scale if up_dequant_scale is None else up_dequant_scale), _ptr(col_scale_il),
+            float(out_quant_scale) if out_quant_scale is not None else 0.0,
+            _default_div_mode if div_mode is None else div_mode, _stream(dev))
+    _check(rc)
+    _launches += 1
+    return out
 
 
 def add_rmsnorm_quant(

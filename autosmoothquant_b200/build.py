@@ -39,18 +39,41 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > built for p in SOURCES + HEADERS)
 
 
+N_KERNEL_TUS = 6  # asq_kernels.cu is compiled once per kernel instantiation (-DASQ_TU=1..6) + once for the host side (0)
+OBJ_DIR = Path(os.environ.get("ASQ_OBJ_DIR", "/tmp/asq_b200_obj"))  # objects stay out of the tree
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the library if it is missing or older than its sources."""
+    """Compile the library if it is missing or older than its sources.  The translation units (one per
+    instantiation of the big kernel, the host side, the glue kernels) are compiled in parallel, then linked."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, SOURCES)]
+    nvcc = find_nvcc()
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-c"]
     if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        compile_flags += ["-Xptxas", "-v"]
+    jobs = []
+    kernels_cu, glue_cu = SOURCES
+    for tu in range(N_KERNEL_TUS + 1):
+        obj = OBJ_DIR / f"asq_kernels_tu{tu}.o"
+        jobs.append((obj, [nvcc, *compile_flags, f"-DASQ_TU={tu}", "-o", str(obj), str(kernels_cu)]))
+    obj = OBJ_DIR / "asq_glue.o"
+    jobs.append((obj, [nvcc, *compile_flags, "-o", str(obj), str(glue_cu)]))
+    procs = [(obj, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for obj, cmd in jobs]
+    logs = []
+    for obj, cmd, proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{out}")
+        logs.append(out)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB_PATH),
+            *[str(obj) for obj, _ in jobs]]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+        raise RuntimeError(f"link failed:\n{' '.join(link)}\n{res.stdout}\n{res.stderr}")
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 

@@ -46,7 +46,7 @@ constexpr int SYNC_AMAX = 8190;      // per-tensor dynamic: bit pattern of the r
 constexpr int SYNC_AMAX_CNT = 8191;  // ... and the number of warps that contributed
 constexpr int SYNC_EXIT = 0;                          // sync[0]: CTAs that finished; sync[1+p]: rows ready in panel p
 
-enum EpiKind : int { EPI_DEQUANT = 0, EPI_RAW_I32 = 1, EPI_ALPHA_BETA = 2 };
+enum EpiKind : int { EPI_DEQUANT = 0, EPI_RAW_I32 = 1, EPI_ALPHA_BETA = 2, EPI_SWIGLU = 3 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -73,6 +73,11 @@ struct LinearParams {
   const void* bias_any;  // EPI_ALPHA_BETA bias (int8 / int32 / fp32)
   float dequant_scale, alpha, beta;
   float out_fq_scale, inv_out_fq_scale;  // != 0: fake-quantise the output through e4m3 (FP8LinearStatic, linear.py:562-564)
+  // EPI_SWIGLU: w rows interleave 32 gate rows with the 32 matching up rows; the epilogue emits
+  // a = T(T(silu(gate)) * up) as T (y_dtype 16-bit) or sat(rint(T(a / out_quant_scale))) as int8, [M, N/2]
+  float out_quant_scale, inv_out_quant_scale;
+  float dequant_scale_up;  // scalar dequant scale of the up columns (gate uses dequant_scale) when col_scale == NULL
+  int mid_dtype;  // T: the activation dtype gate / up / a are rounded to (ASQ_BF16 | ASQ_F16)
   int M, N, K;
   int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
   int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;  // num_n_blocks = TILE_N-wide tiles per row
@@ -401,12 +406,12 @@ __device__ __forceinline__ float round_out(float v, int y_dtype) {
 // fp32 rounding (no FMA contraction), so the result is bit-identical to eager torch.
 template <bool FP8>
 __device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (&v)[32], int col0, float rs,
-                                                const LinearParams& p) {
+                                                const LinearParams& p, float dequant_scale) {
   const int N = p.N;
-  if (p.epi_kind == EPI_DEQUANT) {
+  if (p.epi_kind != EPI_ALPHA_BETA) {
     const bool per_token = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN ||
                             p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC);
-    const float f_scalar = per_token ? __fmul_rn(p.dequant_scale, rs) : p.dequant_scale;
+    const float f_scalar = per_token ? __fmul_rn(dequant_scale, rs) : dequant_scale;
     if (p.col_scale != nullptr) {
       float cs[32];
       load_cols32(p.col_scale, col0, N, cs);
@@ -458,10 +463,73 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (
   }
 }
 
+template <bool FP8>
+__device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (&v)[32], int col0, float rs,
+                                                const LinearParams& p) {
+  epilogue_values<FP8>(r, v, col0, rs, p, p.dequant_scale);
+}
+
 // 32 fp32 results -> packed output words of the requested type (w[] holds 32 * elem_size / 4 words).
 __device__ __forceinline__ void pack_out16(const float (&v)[32], uint32_t (&w)[16], bool bf) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) w[j] = bf ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : pack_f16x2(v[2 * j], v[2 * j + 1]);
+}
+
+// EPI_SWIGLU: vg / vu = dequantised (fp32) gate and up values of the same 32 logical columns.  Follows the eager
+// chain T(gate), T(up) -> T(silu) -> T(* up) [-> T(/ quant_scale) -> rint -> saturate] with the same
+// arithmetic as asq_glue.cu's silu_mul_vec (SFU exp / reciprocal), so the fused epilogue and the stand-alone
+// producer kernel emit identical bytes.  BF / OUT are compile-time so the 32 elements are straight-line code:
+// every rounding to T is a packed F2FP (two values per instruction) followed by a shift / mask unpack.
+//   OUT 0: w[16] = the product as T;  OUT 1: w[8] = int8, division as reciprocal multiply;  OUT 2: int8, IEEE division
+template <bool BF>
+__device__ __forceinline__ void round_pair(float& a, float& b) {
+  if (BF) {
+    const uint32_t w = pack_bf16x2(a, b);
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xFFFF0000u);
+  } else {
+    uint32_t w = pack_f16x2(a, b);
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    a = f.x;
+    b = f.y;
+  }
+}
+template <bool BF, int OUT>
+__device__ __forceinline__ void swiglu_chunk(const float (&vg)[32], const float (&vu)[32], uint32_t* w, const LinearParams& p) {
+  const float qs = p.out_quant_scale, inv = p.inv_out_quant_scale;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float g0 = vg[4 * j + 2 * h], g1 = vg[4 * j + 2 * h + 1], u0 = vu[4 * j + 2 * h], u1 = vu[4 * j + 2 * h + 1];
+      round_pair<BF>(g0, g1);
+      round_pair<BF>(u0, u1);
+      float s0 = __fdividef(g0, 1.0f + __expf(-g0)), s1 = __fdividef(g1, 1.0f + __expf(-g1));
+      round_pair<BF>(s0, s1);
+      float a0 = __fmul_rn(s0, u0), a1 = __fmul_rn(s1, u1);
+      if (OUT == 0) {
+        w[2 * j + h] = BF ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
+      } else {
+        round_pair<BF>(a0, a1);
+        float t0 = OUT == 1 ? __fmul_rn(a0, inv) : __fdiv_rn(a0, qs), t1 = OUT == 1 ? __fmul_rn(a1, inv) : __fdiv_rn(a1, qs);
+        round_pair<BF>(t0, t1);
+        t[2 * h] = t0;
+        t[2 * h + 1] = t1;
+      }
+    }
+    if (OUT != 0) w[j] = cvt_s8x4(t[0], t[1], t[2], t[3]);
+  }
+}
+__device__ __forceinline__ void swiglu_dispatch(const float (&vg)[32], const float (&vu)[32], uint32_t* w, const LinearParams& p) {
+  const bool bf = (p.mid_dtype == ASQ_BF16);
+  if (p.y_dtype != ASQ_I8) {
+    if (bf) swiglu_chunk<true, 0>(vg, vu, w, p); else swiglu_chunk<false, 0>(vg, vu, w, p);
+  } else if (p.div_mode == ASQ_DIV_RECIPROCAL) {
+    if (bf) swiglu_chunk<true, 1>(vg, vu, w, p); else swiglu_chunk<false, 1>(vg, vu, w, p);
+  } else {
+    if (bf) swiglu_chunk<true, 2>(vg, vu, w, p); else swiglu_chunk<false, 2>(vg, vu, w, p);
+  }
 }
 
 // Fallback store (odd N, int8 output, ...): direct global writes, predicated per element.
@@ -847,9 +915,10 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t stage_base = base + Cfg::EPI_OFFSET + ew * (EPI_BUF_BYTES * EPI_NBUF);
     const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
     const bool staged = p.tma_store != 0;
-    const int elem = out16 ? 2 : 4;
+    const int elem = out16 ? 2 : (p.y_dtype == ASQ_I8 ? 1 : 4);
     const bool per_token_epi = (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN ||
-                                p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC) && p.epi_kind == EPI_DEQUANT;
+                                p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC) &&
+                               (p.epi_kind == EPI_DEQUANT || p.epi_kind == EPI_SWIGLU);
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     int it = 0;
     TileWalk walk(p, worker, num_workers);
@@ -883,6 +952,53 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       if (it == 0 && ew == 0 && lane == 0) ASQ_STAMP(5);
       if (per_token_epi && row < p.M) rs = __ldcg(p.row_scale + row);
+      if (p.epi_kind == EPI_SWIGLU) {
+        // Interleaved gate|up tile: group g = 32 gate columns + the 32 matching up columns -> 32 outputs.  This
+        // warp takes groups 2*half and 2*half+1, i.e. 64 adjacent output columns of its 32 rows: one staging
+        // tile (int8: 32 rows x 64 B, dense; 16-bit: 32 rows x 128 B, swizzled) and one TMA store per tile.
+        const int g_first = 2 * half;
+        if (g_first < ngroups) {
+          const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+          if (gcount >= EPI_NBUF) {
+            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int gi = 0; gi < 2 && g_first + gi < ngroups; ++gi) {
+            const int g = g_first + gi;
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr0 + g * UNIT_N, r0);
+            tmem_ld_32x32(taddr0 + g * UNIT_N + 32, r1);
+            tmem_ld_wait();
+            float vg[32], vu[32];
+            epilogue_values<FP8>(r0, vg, tile_col0 + g * UNIT_N, rs, p, p.dequant_scale);
+            epilogue_values<FP8>(r1, vu, tile_col0 + g * UNIT_N + 32, rs, p, p.dequant_scale_up);
+            uint32_t w[16];
+            swiglu_dispatch(vg, vu, w, p);
+            if (out16) {
+              stage_words<16>(buf, lane, gi * 4, w);
+            } else {
+              const uint32_t addr = buf + lane * 64 + gi * 32;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 16), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tma_store_2d(&tmY, buf, ((tile_col0 >> 1) + g_first * 32) * elem, row0);
+            tma_store_commit();
+          }
+          ++gcount;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+          else         mbar_arrive(tempty_bar(acc));
+        }
+        continue;
+      }
       int chunk_pair = 0;  // index of the (r0, r1) pair inside this warp's stream-K region
 #pragma unroll 1
       for (int g = half; g < ngroups; g += 2, ++chunk_pair) {
@@ -1033,6 +1149,9 @@ __global__ void __launch_bounds__(256) asq_quantize_kernel(const LinearParams p)
 
 }  // namespace asq
 
+int asq_glue_fail(int code, const char* fmt, ...);  // formats into the thread-local error buffer (host TU)
+
+#if !defined(ASQ_TU) || ASQ_TU == 0
 // ====================================================================== host side
 namespace {
 
@@ -1070,8 +1189,7 @@ struct DeviceState {
   int sm_count = 0;
   bool attrs_set = false;
 };
-constexpr int kMaxDevices = 64;
-DeviceState g_dev[kMaxDevices];
+DeviceState g_dev[64];
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 
@@ -1082,7 +1200,7 @@ int get_device(int* dev_out, DeviceState** st_out) {
     cudaGetLastError();
     return fail(ASQ_ERR_CUDA, "no CUDA device available: %s", cudaGetErrorString(e));
   }
-  if (dev < 0 || dev >= kMaxDevices) return fail(ASQ_ERR_CUDA, "device index %d out of range", dev);
+  if (dev < 0 || dev >= 64) return fail(ASQ_ERR_CUDA, "device index %d out of range", dev);
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceState& st = g_dev[dev];
   if (!st.probed) {
@@ -1119,6 +1237,19 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t K, int box
   return ASQ_OK;
 }
 
+// Dense (unswizzled) map over a row-major [rows, row_bytes] byte matrix, box = [box_rows, box_bytes].
+int make_tmap_plain(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t row_bytes, int box_bytes, int box_rows) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(row_bytes), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(row_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                        estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ASQ_ERR_CUDA, "cuTensorMapEncodeTiled (plain) failed (%d)", static_cast<int>(r));
+  return ASQ_OK;
+}
+
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
@@ -1150,6 +1281,16 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
   return kFixedBytes + rs + aq;
 }
 
+}  // namespace
+#endif  // ASQ_TU host part
+
+// ---------------------------------------------------------------------- kernel launchers
+// The six instantiations of the kernel dominate the build time, so the build compiles this file once per
+// instantiation in parallel (-DASQ_TU=1..6: only the kernel + its launcher) plus once for the host side
+// (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
+namespace asq_launch {
+constexpr int kMaxDevices = 64;
+
 template <bool FP8, int CG, int MC>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBu, const CUtensorMap& tmY,
                const asq::LinearParams& p, int workers, cudaStream_t stream) {
@@ -1162,7 +1303,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     cudaGetDevice(&dev);
     if (!attr_set[dev]) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-      if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      if (e != cudaSuccess) return asq_glue_fail(ASQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr_set[dev] = true;
     }
   }
@@ -1180,7 +1321,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBu, tmY, p);
-  if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return asq_glue_fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
 }
 
@@ -1215,6 +1356,43 @@ int max_multicast_clusters(int dev) {
   known[dev] = true;
   return n;
 }
+
+#if defined(ASQ_TU)
+#if ASQ_TU == 0
+#define ASQ_LAUNCH_DECL extern template
+#else
+#define ASQ_LAUNCH_DECL template
+#endif
+#define ASQ_LAUNCH_INST(FP8, CG, MC)                                                                            \
+  ASQ_LAUNCH_DECL int launch_cfg<FP8, CG, MC>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,        \
+                                              const CUtensorMap&, const asq::LinearParams&, int, cudaStream_t);
+#if ASQ_TU == 0 || ASQ_TU == 1
+ASQ_LAUNCH_INST(false, 1, 1)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 2
+ASQ_LAUNCH_INST(false, 2, 1)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 3
+ASQ_LAUNCH_INST(true, 1, 1)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 4
+ASQ_LAUNCH_INST(true, 2, 1)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 5
+ASQ_LAUNCH_INST(false, 2, 2)
+ASQ_LAUNCH_DECL int max_multicast_clusters<false>(int);
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 6
+ASQ_LAUNCH_INST(true, 2, 2)
+ASQ_LAUNCH_DECL int max_multicast_clusters<true>(int);
+#endif
+#endif  // ASQ_TU
+}  // namespace asq_launch
+
+#if !defined(ASQ_TU) || ASQ_TU == 0
+namespace {
+using asq_launch::launch_cfg;
+using asq_launch::max_multicast_clusters;
 
 // CTA pairs (256-row tiles) whenever there is more than one 128-row panel.  ASQ_FORCE_CG=1|2 overrides
 // the pairing (profiling / tests).
@@ -1261,7 +1439,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     static int mc_env = -1;
     if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     const int want = mc_env ? mc_env : 1;
-    if (want == 2 && cg == 2 && p.N > asq::TILE_N) {
+    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU) {
       const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
       const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
       if (clusters > 0 && super_tiles >= clusters) mc = 2;
@@ -1363,11 +1541,17 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   memset(&tmY, 0, sizeof(tmY));
   {
     const int elem = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16) ? 2 : (p.y_dtype == ASQ_I8 ? 1 : 4);
-    const long long row_bytes = static_cast<long long>(p.N) * elem;
+    const bool swiglu = (p.epi_kind == asq::EPI_SWIGLU);  // output is [M, N/2]
+    const long long row_bytes = static_cast<long long>(swiglu ? p.N / 2 : p.N) * elem;
     static int no_tma_store = -1;
     if (no_tma_store < 0) { const char* e = getenv("ASQ_NO_TMA_STORE"); no_tma_store = (e != nullptr && e[0] == '1'); }
     p.tma_store = (!no_tma_store && elem != 1 && row_bytes % 16 == 0) ? 1 : 0;
-    if (p.tma_store) {
+    if (swiglu) {
+      p.tma_store = 1;  // the SwiGLU epilogue only exists as a staged store
+      if (row_bytes % 16 != 0) return fail(ASQ_ERR_INVALID, "swiglu: output row pitch (%lld bytes) must be a multiple of 16", row_bytes);
+      rc = (elem == 1) ? make_tmap_plain(&tmY, p.y, p.M, row_bytes, 64, 32) : make_tmap(&tmY, p.y, p.M, row_bytes, 32);
+      if (rc != ASQ_OK) return rc;
+    } else if (p.tma_store) {
       rc = make_tmap(&tmY, p.y, p.M, row_bytes, 32);
       if (rc != ASQ_OK) return rc;
     } else {
@@ -1494,6 +1678,30 @@ int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w
   return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream));
 }
 
+int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const int8_t* w_il, const float* bias_il,
+                              void* out, int out_dtype, int mid_dtype, int64_t M, int64_t N, int64_t K,
+                              float gate_dequant_scale, float up_dequant_scale, const float* col_scale_il,
+                              float out_quant_scale, int div_mode, void* stream) {
+  int rc = check_common(xq, w_il, out, M, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (N % 64 != 0) return fail(ASQ_ERR_INVALID, "swiglu: N=%lld (2 x intermediate) must be a multiple of 64", (long long)N);
+  if (mid_dtype != ASQ_BF16 && mid_dtype != ASQ_F16) return fail(ASQ_ERR_INVALID, "swiglu: mid_dtype must be f16 or bf16");
+  if (out_dtype != ASQ_I8 && out_dtype != mid_dtype) return fail(ASQ_ERR_INVALID, "swiglu: out_dtype must be i8 or equal mid_dtype");
+  if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
+  if (out_dtype == ASQ_I8 && !(out_quant_scale > 0.f)) return fail(ASQ_ERR_INVALID, "swiglu: out_quant_scale must be positive");
+  if (M == 0) return ASQ_OK;
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = out; p.bias = bias_il; p.col_scale = col_scale_il;
+  p.dequant_scale = gate_dequant_scale; p.dequant_scale_up = up_dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = out_dtype; p.mid_dtype = mid_dtype; p.epi_kind = asq::EPI_SWIGLU; p.div_mode = div_mode;
+  p.out_quant_scale = out_quant_scale; p.inv_out_quant_scale = out_dtype == ASQ_I8 ? 1.0f / out_quant_scale : 0.f;
+  p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
+  p.row_scale = const_cast<float*>(row_scale);
+  return launch_linear(false, xq, w_il, p, static_cast<cudaStream_t>(stream));
+}
+
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c, int64_t M, int64_t N, int64_t K,
                    void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(a, w, c, M, N, K);
@@ -1563,3 +1771,4 @@ int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale, int6
 }
 
 }  // extern "C"
+#endif  // ASQ_TU host part

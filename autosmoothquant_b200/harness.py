@@ -171,6 +171,19 @@ class QuantDecoderLayer(nn.Module):
             del self.q_proj, self.k_proj, self.v_proj, self.gate_proj, self.up_proj
             self.fused = True
 
+    def enable_swiglu_epilogue(self) -> None:
+        """Re-lay the fused gate|up weight out for the SwiGLU epilogue (32-row blocks of gate and up interleaved,
+        `_lib.interleave_gate_up`); the glue forward then needs no gate|up tensor and no SiLU kernel."""
+        assert self.fused and self.cfg.intermediate % 32 == 0
+        from . import _lib
+
+        mod = self.gate_up_proj
+        I = mod.weight.shape[0] // 2
+        w_il = _lib.interleave_gate_up(mod.weight[:I], mod.weight[I:])
+        b_il = _lib.interleave_gate_up(mod.bias[:I], mod.bias[I:]) if mod.use_bias else None
+        gate_scale, up_scale = (float(getattr(mod, n).item()) for n in mod._scale_names[:2])
+        self.gate_up_il = (w_il, b_il, gate_scale, up_scale)
+
     def linears(self):
         if self.fused:
             return [self.qkv_proj, self.o_proj, self.gate_up_proj, self.down_proj]
@@ -225,12 +238,18 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     # row-parallel wrapper, whose forward ends with the all-reduce
     o = layer.o_proj(attn.transpose(1, 2).reshape(B * S, nq * hd))
     x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
-    gu_mod = layer.gate_up_proj
-    gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
-                             col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
     tp_world = getattr(layer, "tp_world", 1)
     down = layer.down_proj.shard if tp_world > 1 else layer.down_proj
-    a8, _ = _lib.silu_mul_quant(gu, float(down.quant_scale.item()))
+    il = getattr(layer, "gate_up_il", None)
+    if il is not None:
+        # SiLU(gate)*up and down_proj's activation quantisation run in the gate|up GEMM epilogue
+        a8 = _lib.w8a8_gateup_swiglu(q8, il[0], il[1], il[2], up_dequant_scale=il[3],
+                                     out_quant_scale=float(down.quant_scale.item()), mid_dtype=x2.dtype)
+    else:
+        gu_mod = layer.gate_up_proj
+        gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
+                                 col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
+        a8, _ = _lib.silu_mul_quant(gu, float(down.quant_scale.item()))
     d = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
                             out_dtype=x2.dtype)
     if tp_world > 1:  # row-parallel partial sums -> one all-reduce over NVLink
@@ -245,7 +264,7 @@ class QuantDecoder(nn.Module):
 
     def __init__(self, cfg: DecoderConfig, quant_config: Optional[Dict[str, str]] = None, device="cuda",
                  dtype=torch.bfloat16, seed: int = 0, layers: Optional[int] = None, fuse_projections: bool = False,
-                 glue: bool = False):
+                 glue: bool = False, swiglu_epilogue: bool = True):
         super().__init__()
         self.cfg = cfg
         self.qcfg = normalise_quant_config(quant_config or {})
@@ -260,6 +279,9 @@ class QuantDecoder(nn.Module):
             self.embed.weight.normal_(0.0, 1.0, generator=gen)
         self.layers = nn.ModuleList(QuantDecoderLayer(cfg, self.qcfg, gen, device, dtype, fuse_projections)
                                     for _ in range(n_layers))
+        if self.glue and swiglu_epilogue and cfg.intermediate % 32 == 0:
+            for layer in self.layers:
+                layer.enable_swiglu_epilogue()
         self.register_buffer("norm_weight", torch.ones(cfg.hidden, dtype=dtype, device=device))
         self.lm_head = nn.Linear(cfg.hidden, cfg.vocab, bias=False, device=device, dtype=dtype)
         with torch.no_grad():

@@ -212,13 +212,15 @@ def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: O
     from . import harness
 
     model = harness.QuantDecoder(cfg, quant_config, device=device, dtype=dtype, seed=seed, layers=layers,
-                                 fuse_projections=True, glue=glue)
+                                 fuse_projections=True, glue=glue, swiglu_epilogue=False)
     if model.qcfg["type"] != "int8":
         raise NotImplementedError("tensor-parallel fp8 stack")
     for layer in model.layers:
         layer.qkv_proj = _shard_fused_columns(layer.qkv_proj, rank, world, device)
         layer.qkv_sizes = list(layer.qkv_proj.qkv_size)
         layer.gate_up_proj = _shard_fused_columns(layer.gate_up_proj, rank, world, device)
+        if model.glue and (cfg.intermediate // world) % 32 == 0:
+            layer.enable_swiglu_epilogue()  # interleave the LOCAL gate / up rows for the SwiGLU epilogue
         for name in ("o_proj", "down_proj"):
             full = getattr(layer, name)
             setattr(layer, name, RowParallelLinear(shard_row(full, rank, world).to(device), group=group,

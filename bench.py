@@ -300,7 +300,7 @@ def run_ours(args, cfg, layers):
     lin_time, lin_ops, n_lin = 0.0, 0.0, 0
     if True:
         events = []
-        originals = {name: getattr(_lib, name) for name in ("w8a8_linear", "w8a8_linear_q8", "fp8_linear")}
+        originals = {name: getattr(_lib, name) for name in ("w8a8_linear", "w8a8_linear_q8", "fp8_linear", "w8a8_gateup_swiglu")}
 
         def timed(fn):
             def wrapper(x, weight, *a, **kw):
@@ -308,7 +308,8 @@ def run_ours(args, cfg, layers):
                 s.record()
                 out = fn(x, weight, *a, **kw)
                 e.record()
-                events.append((s, e, 2.0 * x.shape[0] * x.shape[1] * weight.shape[0]))
+                events.append((s, e, 2.0 * x.shape[0] * x.shape[1] * weight.shape[0],
+                               (fn.__name__, x.shape[0], weight.shape[0], x.shape[1])))
                 return out
             return wrapper
 
@@ -326,10 +327,16 @@ def run_ours(args, cfg, layers):
         finally:
             for name, fn in originals.items():
                 setattr(_lib, name, fn)
-        for s, e, ops in events:
-            lin_time += s.elapsed_time(e) * 1e-3
+        by_shape = {}
+        for s, e, ops, key in events:
+            dt = s.elapsed_time(e) * 1e-3
+            lin_time += dt
             lin_ops += ops
             n_lin += 1
+            agg = by_shape.setdefault(key, [0, 0.0, 0.0])
+            agg[0] += 1
+            agg[1] += dt
+            agg[2] += ops
 
     t = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device=dev)
     if world > 1:
@@ -365,10 +372,11 @@ def run_ours(args, cfg, layers):
                             f"batch {args.batch} x seq {S} per GPU, bf16 activations",
                 "layers": layers, "global_batch": B * replicas, "seq_len": S,
                 "parallelism": f"{args.parallel}{world}", "cuda_graph": graph is not None,
-                "projections": "q|k|v and gate|up fused per layer via W8A8BFP32OFP32QKVLinear (4 launches/layer)"
+                "projections": "q|k|v and gate|up fused per layer (4 GEMM launches/layer)"
                                if not args.no_fuse else "one launch per projection (7 launches/layer)",
-                "glue": ("add+RMSNorm->int8, SiLU*up->int8 and in-place RoPE kernels feed the GEMMs (asq_glue.cu); "
-                         "o_proj quantises in-kernel") if getattr(model, "glue", False)
+                "glue": ("add+RMSNorm->int8 and in-place RoPE kernels feed the GEMMs (asq_glue.cu); SiLU(gate)*up and "
+                         "down_proj's quantisation run in the gate|up GEMM epilogue; o_proj quantises in-kernel")
+                        if getattr(model, "glue", False)
                         else "torch norms / RoPE / SiLU; every linear quantises its own input in-kernel",
                 "l2": "weights (6.6 GB int8) and activations stream through the 126 MB L2 every step: inputs larger than L2",
                 "wall_s_timed_region": t_wall,
@@ -383,6 +391,9 @@ def run_ours(args, cfg, layers):
                 "kernel": "asq_linear_kernel<int8,256>", "launches_timed": n_lin,
                 "peak_source": peak_src,
                 "linear_share_of_step": (lin_time / (t_dev / args.steps)) if lin_time else None,
+                "by_launch_shape": [{"entry": k[0], "M": k[1], "N": k[2], "K": k[3], "launches": v[0],
+                                     "avg_us": v[1] / v[0] * 1e6, "tops": v[2] / v[1] / 1e12}
+                                    for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])],
             },
         }
         if world == 1 and not args.no_cpu_baseline:

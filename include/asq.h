@@ -148,6 +148,23 @@ int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w
                        float dequant_scale, const float* col_scale,
                        void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
+/* gate|up projection with the SwiGLU product (and the next Linear's activation quantisation) in the GEMM
+ * epilogue: the [M, 2I] gate|up tensor of HF LlamaMLP.forward (borrowed at models/llama.py:218) never
+ * reaches HBM.  Replaces asq_w8a8_linear_q8 (fused gate|up) + asq_silu_mul_quant byte for byte.
+ *   w_il  [N = 2I, K] int8, rows INTERLEAVED in blocks of 32: rows [64b, 64b+32) = gate rows [32b, 32b+32),
+ *         rows [64b+32, 64b+64) = up rows [32b, 32b+32)   (a load-time re-layout; I % 32 == 0)
+ *   gate_dequant_scale / up_dequant_scale  the two projections keep their own scalar scale (as the blocks of
+ *         the fused module do, linear.py:197-200); col_scale_il [N] fp32, if not NULL, replaces both with a
+ *         per-column vector; bias_il [N] fp32 or NULL; vectors are in the same interleaved order as w_il
+ *   gate = T(f * acc_g (+ b)), up = T(f * acc_u (+ b)), a = T(T(silu(gate)) * up), T = mid_dtype (F16 | BF16)
+ *   out   [M, I]: out_dtype == mid_dtype -> a;  ASQ_I8 -> sat(rint(T(a / out_quant_scale))), which is what
+ *         W8A8BFP32OFP32LinearWithQuantScale (per-tensor) derives from a (linear.py:290-292)
+ *   row_scale [M] fp32 or NULL: per-token scales of xq                                            */
+int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const int8_t* w_il, const float* bias_il,
+                              void* out, int out_dtype, int mid_dtype, int64_t M, int64_t N, int64_t K,
+                              float gate_dequant_scale, float up_dequant_scale, const float* col_scale_il,
+                              float out_quant_scale, int div_mode, void* stream);
+
 /* c[M,N] (int32) = a[M,K] (int8) . w[N,K]^T (int8), exact.  Drop-in for
  * I8CUGEMM::linear_a8_w8_o32_ and the exactness tap of the fused kernels. */
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c,

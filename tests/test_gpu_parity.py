@@ -423,6 +423,72 @@ def test_linear_q8_equals_module_path(exact_div):
     assert torch.equal(y3, y4)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,I,K,per_token,bias", [(300, 96, 256, False, True), (512, 1376, 1024, False, False),
+                                                  (77, 160, 512, True, True), (2048, 11008, 4096, False, False)])
+@pytest.mark.parametrize("div", ["exact", "reciprocal"])
+def test_gateup_swiglu_epilogue_equals_two_launch_path(dtype, M, I, K, per_token, bias, div):
+    """SiLU(gate)*up (+ down_proj's per-tensor quantisation) in the gate|up GEMM epilogue must emit exactly the
+    bytes of the two-launch path it replaces (fused gate|up GEMM -> silu_mul_quant), which in turn is tied to
+    the oracle by test_silu_mul_quant / test_fused_linear_vs_oracle.  Covers M / N tile tails (I = 96 -> one
+    192-wide tile, I = 160 -> 256 + 64), per-token input scales and bias."""
+    if M * I * K > 2 ** 33 and (dtype == "f16" or div == "exact"):
+        pytest.skip("full-size case runs once")
+    g = torch.Generator().manual_seed(I + M)
+    td = TORCH_DT[dtype]
+    xq = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(DEV)
+    wg = torch.randint(-127, 128, (I, K), dtype=torch.int8, generator=g).to(DEV)
+    wu = torch.randint(-127, 128, (I, K), dtype=torch.int8, generator=g).to(DEV)
+    sg, su = 2.9e-6 * (4096 / K) ** 0.5, 4.3e-6 * (4096 / K) ** 0.5  # gate / up keep their own dequant scale
+    cs = torch.cat([torch.full((I,), sg), torch.full((I,), su)]).to(DEV)
+    b = (torch.randn(2 * I, generator=g) * 0.5).to(DEV) if bias else None
+    rs = (torch.rand(M, generator=g) * 2 + 0.5).to(DEV) if per_token else None
+    qs = 0.0431
+    mode = L.DIV_EXACT if div == "exact" else L.DIV_RECIPROCAL
+    gu = L.w8a8_linear_q8(xq, torch.cat([wg, wu]).contiguous(), b, 1.0, col_scale=cs, row_scale=rs, out_dtype=td)
+    q_want, a_want = L.silu_mul_quant(gu, qs, want_q=True, want_a=True, div_mode=mode)
+    w_il = L.interleave_gate_up(wg, wu)
+    cs_il = L.interleave_gate_up(cs[:I], cs[I:])
+    b_il = L.interleave_gate_up(b[:I], b[I:]) if bias else None
+    q_got = L.w8a8_gateup_swiglu(xq, w_il, b_il, 1.0, col_scale_il=cs_il, row_scale=rs, out_quant_scale=qs,
+                                 mid_dtype=td, div_mode=mode)
+    a_got = L.w8a8_gateup_swiglu(xq, w_il, b_il, 1.0, col_scale_il=cs_il, row_scale=rs, out_quant_scale=None, mid_dtype=td)
+    torch.cuda.synchronize()
+    assert q_got.dtype == torch.int8 and q_got.shape == (M, I) and a_got.dtype == td
+    assert float(a_want.float().abs().max()) > 0.5 and int(q_want.abs().max()) > 20  # the data exercise the range
+    assert torch.equal(a_got, a_want), f"product differs in {(a_got != a_want).sum().item()} elements"
+    assert torch.equal(q_got, q_want), f"int8 differs in {(q_got != q_want).sum().item()} elements"
+    # the two scalar dequant scales instead of the per-column vector
+    q2 = L.w8a8_gateup_swiglu(xq, w_il, b_il, sg, up_dequant_scale=su, row_scale=rs, out_quant_scale=qs, mid_dtype=td,
+                              div_mode=mode)
+    assert torch.equal(q2, q_want)
+    q3 = L.w8a8_gateup_swiglu(xq, w_il, b_il, sg, row_scale=rs, out_quant_scale=qs, mid_dtype=td, div_mode=mode)
+    gu3 = L.w8a8_linear_q8(xq, torch.cat([wg, wu]).contiguous(), b, sg, row_scale=rs, out_dtype=td)
+    assert torch.equal(q3, L.silu_mul_quant(gu3, qs, div_mode=mode)[0])
+
+
+def test_gateup_swiglu_rejects_bad_arguments():
+    xq = torch.zeros((4, 64), dtype=torch.int8, device=DEV)
+    w = torch.zeros((96, 64), dtype=torch.int8, device=DEV)  # N = 96 is not a multiple of 64
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        L.w8a8_gateup_swiglu(xq, w, None, 1.0, out_quant_scale=0.1)
+    w = torch.zeros((128, 64), dtype=torch.int8, device=DEV)
+    with pytest.raises(RuntimeError, match="positive"):
+        L.w8a8_gateup_swiglu(xq, w, None, 1.0, out_quant_scale=0.0)
+    assert L.w8a8_gateup_swiglu(xq[:0], w, None, 1.0, out_quant_scale=0.1).shape == (0, 64)
+
+
+def test_glue_stack_swiglu_epilogue_is_bit_identical():
+    """The decoder forward with the SwiGLU epilogue == the same forward with the separate SiLU kernel."""
+    from autosmoothquant_b200 import harness
+
+    ids = torch.randint(0, harness.TINY.vocab, (2, 96), generator=torch.Generator().manual_seed(1)).to(DEV)
+    a = harness.QuantDecoder(harness.TINY, {}, device=DEV, seed=5, fuse_projections=True, glue=True, swiglu_epilogue=False)
+    b = harness.QuantDecoder(harness.TINY, {}, device=DEV, seed=5, fuse_projections=True, glue=True, swiglu_epilogue=True)
+    assert hasattr(b.layers[0], "gate_up_il") and not hasattr(a.layers[0], "gate_up_il")
+    assert torch.equal(a(ids, last_token_only=False), b(ids, last_token_only=False))
+
+
 def test_glue_stack_close_to_module_stack():
     """Whole tiny decoder: producer-fused path vs module path.  Not bit-identical by construction (the fp32
     variance is summed in a different order), so compare logits with a tolerance."""
