@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = (
     "asq_quantize_act",
     "asq_w8a8_linear_q8",
     "asq_w8a8_gateup_swiglu_q8",
+    "asq_w8a8_linear_q8_rope",
     "asq_add_rmsnorm_quant",
     "asq_silu_mul_quant",
     "asq_rope_inplace",
@@ -117,6 +118,9 @@ def load():
         lib.asq_w8a8_gateup_swiglu_q8.restype = c_i
         lib.asq_w8a8_gateup_swiglu_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i64, c_i64, c_i64, c_f, c_f,
                                                   c_vp, c_f, c_i, c_vp]
+        lib.asq_w8a8_linear_q8_rope.restype = c_i
+        lib.asq_w8a8_linear_q8_rope.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
+                                                c_vp, c_vp, c_i64, c_i64, c_i64, c_i, c_vp]
         lib.asq_add_rmsnorm_quant.restype = c_i
         lib.asq_add_rmsnorm_quant.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_f, c_vp]
         lib.asq_silu_mul_quant.restype = c_i
@@ -388,8 +392,12 @@ def w8a8_linear_q8(
     col_scale: Optional[torch.Tensor] = None,
     row_scale: Optional[torch.Tensor] = None,
     out_dtype: torch.dtype = torch.bfloat16,
+    rope: Optional[tuple] = None,
 ) -> torch.Tensor:
-    """INT8 GEMM + dequant epilogue for activations a fused producer already quantised (no prologue)."""
+    """INT8 GEMM + dequant epilogue for activations a fused producer already quantised (no prologue).
+    rope = (cos, sin, S, rope_cols): rotate-half RoPE on columns < rope_cols in the epilogue; cos / sin are the
+    [S, 128] tables in the blocked layout of `rope_tables_blocked`; an optional fifth element True vouches that the
+    tables repeat their first half (HF's cat(freqs, freqs)), which halves the table reads."""
     global _launches
     dev = _require_cuda(xq, weight, bias, col_scale, row_scale)
     if xq.dtype != torch.int8 or weight.dtype != torch.int8 or xq.dim() != 2 or xq.shape[1] != weight.shape[1]:
@@ -402,6 +410,21 @@ def w8a8_linear_q8(
     if M == 0:
         return y
     lib = load()
+    if rope is not None:
+        cos, sin, S, rope_cols = rope[:4]
+        halves_equal = bool(rope[4]) if len(rope) > 4 else False
+        _require_cuda(cos, sin)
+        if cos.dtype != out_dtype or sin.dtype != out_dtype or cos.shape != sin.shape or cos.dim() != 3 or not (
+                cos.is_contiguous() and sin.is_contiguous()) or cos.shape[1] != S or cos.shape[2] != 8:
+            raise ValueError("rope tables must be rope_tables_blocked() outputs [head_dim/8, S, 8] of the output dtype")
+        with torch.cuda.device(dev):
+            rc = lib.asq_w8a8_linear_q8_rope(xq.data_ptr(), _ptr(row_scale), weight.data_ptr(), _ptr(bias), y.data_ptr(),
+                                             _code(out_dtype), M, N, K, float(dequant_scale), _ptr(col_scale),
+                                             cos.data_ptr(), sin.data_ptr(), int(S), int(rope_cols), cos.shape[0] * 8,
+                                             1 if halves_equal else 0, _stream(dev))
+        _check(rc)
+        _launches += 1
+        return y
     with torch.cuda.device(dev):
         stream = _stream(dev)
         ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(0, 0))
@@ -410,6 +433,12 @@ def w8a8_linear_q8(
     _check(rc)
     _launches += 1
     return y
+
+
+def rope_tables_blocked(table: torch.Tensor) -> torch.Tensor:
+    """[S, head_dim] cos or sin table -> the [head_dim/8, S, 8] layout the RoPE epilogue reads (one-time re-layout)."""
+    S, hd = table.shape
+    return table.reshape(S, hd // 8, 8).transpose(0, 1).contiguous()
 
 
 def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:

@@ -76,6 +76,11 @@ struct LinearParams {
   // EPI_SWIGLU: w rows interleave 32 gate rows with the 32 matching up rows; the epilogue emits
   // a = T(T(silu(gate)) * up) as T (y_dtype 16-bit) or sat(rint(T(a / out_quant_scale))) as int8, [M, N/2]
   float out_quant_scale, inv_out_quant_scale;
+  // RoPE in the epilogue (fused q|k|v projection): columns < rope_cols are rotated per 128-wide head with the
+  // HF rotate-half formula, position = row % rope_S, tables [rope_S, 128] of the output dtype
+  const void* rope_cos;
+  const void* rope_sin;
+  int rope_S, rope_cols, rope_halves_equal;
   float dequant_scale_up;  // scalar dequant scale of the up columns (gate uses dequant_scale) when col_scale == NULL
   int mid_dtype;  // T: the activation dtype gate / up / a are rounded to (ASQ_BF16 | ASQ_F16)
   int M, N, K;
@@ -98,6 +103,7 @@ struct Elem;
 template <>
 struct Elem<float> {
   static constexpr int VEC = 4;  // elements per 16-byte load
+  static constexpr bool IS_BF16 = false;
   __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
     f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
     f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
@@ -107,6 +113,7 @@ struct Elem<float> {
 template <>
 struct Elem<__half> {
   static constexpr int VEC = 8;
+  static constexpr bool IS_BF16 = false;
   __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -121,6 +128,7 @@ struct Elem<__half> {
 template <>
 struct Elem<__nv_bfloat16> {
   static constexpr int VEC = 8;
+  static constexpr bool IS_BF16 = true;
   __device__ static __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -202,25 +210,55 @@ __device__ __forceinline__ float quotient_for_rint(float x, float s, float inv) 
   return r;
 }
 
-template <typename T, bool FP8>
-__device__ __forceinline__ void quantize_vec(const uint4& v, uint8_t* dst, int mode, bool recip, float scale,
-                                             float inv_scale, const LinearParams& p) {
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <bool BF>
+__device__ __forceinline__ void round_pair(float& a, float& b) {
+  if (BF) {
+    const uint32_t w = pack_bf16x2(a, b);
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xFFFF0000u);
+  } else {
+    uint32_t w = pack_f16x2(a, b);
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    a = f.x;
+    b = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void round_pair_t(float& a, float& b) {  // (a, b) -> (f32(T(a)), f32(T(b)))
+  if (sizeof(T) == 2) round_pair<Elem<T>::IS_BF16>(a, b);
+}
+
+// Element arithmetic of the prologue, selected at compile time so the per-vector code is branch-free:
+//   QM_ROUND        q = sat(rint(x))
+//   QM_SCALE_RECIP  q = sat(rint(T(x * (1/qs))))   torch CUDA: tensor / python scalar = multiply by the reciprocal
+//   QM_SCALE_DIV    q = sat(rint(T(x / qs)))       torch CPU: true division
+//   QM_ROW_DIV      q = sat(rint(f32(x) / s))      per-token / caller-supplied row scale: fp32 tensor / fp32 tensor
+//   QM_TENSOR_DYN   q = T(x / s)                   per-tensor dynamic (fp8): T tensor / 0-dim T tensor
+enum QMode : int { QM_ROUND = 0, QM_SCALE_RECIP = 1, QM_SCALE_DIV = 2, QM_ROW_DIV = 3, QM_TENSOR_DYN = 4 };
+
+template <typename T, bool FP8, int QM>
+__device__ __forceinline__ void quantize_vec(const uint4& v, uint8_t* dst, float scale, const LinearParams& p) {
   constexpr int VEC = Elem<T>::VEC;
   float f[VEC];
   Elem<T>::unpack(v, f);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    if (mode == ASQ_ACT_PER_TOKEN || mode == ASQ_ACT_ROW_SCALE_GIVEN) {
-      // fp32 tensor / fp32 tensor: true division on every device
-      // (quotient_for_rint() is exact but measured slower on B200: FRND is a quarter-rate op and the per-element
-      // branch defeats unrolling, so the plain IEEE division is used.)
-      f[i] = (kRecipFastPath && !FP8 && inv_scale != 0.f) ? quotient_for_rint(f[i], scale, inv_scale)
-                                                          : __fdiv_rn(f[i], scale);
-    } else if (mode == ASQ_ACT_SCALE) {
-      f[i] = Elem<T>::round_to(recip ? __fmul_rn(f[i], p.inv_quant_scale) : __fdiv_rn(f[i], p.quant_scale));
-    } else if (mode == ASQ_ACT_PER_TENSOR_DYNAMIC) {
-      f[i] = Elem<T>::round_to(__fdiv_rn(f[i], scale));  // T tensor / 0-dim T tensor: true division, rounded to T
-    }
+  for (int i = 0; i < VEC; i += 2) {
+    float a = f[i], b = f[i + 1];
+    if (QM == QM_ROW_DIV) { a = __fdiv_rn(a, scale); b = __fdiv_rn(b, scale); }
+    else if (QM == QM_SCALE_RECIP) { a = __fmul_rn(a, p.inv_quant_scale); b = __fmul_rn(b, p.inv_quant_scale); round_pair_t<T>(a, b); }
+    else if (QM == QM_SCALE_DIV) { a = __fdiv_rn(a, p.quant_scale); b = __fdiv_rn(b, p.quant_scale); round_pair_t<T>(a, b); }
+    else if (QM == QM_TENSOR_DYN) { a = __fdiv_rn(a, scale); b = __fdiv_rn(b, scale); round_pair_t<T>(a, b); }
+    f[i] = a;
+    f[i + 1] = b;
   }
   pack_store<FP8, VEC>(dst, f);
 }
@@ -251,20 +289,17 @@ __device__ __forceinline__ float token_scale(float amax, const LinearParams& p) 
                                             : Elem<T>::round_to(__fdiv_rn(amax, p.qmax));
 }
 
-template <typename T, bool FP8>
+template <typename T, bool FP8, int QM>
 __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_t* __restrict__ qrow,
-                                              int K, int lane, const LinearParams& p, float given_scale) {
+                                              int K, int lane, const LinearParams& p, float given_scale, bool find_absmax) {
   constexpr int VEC = Elem<T>::VEC;
   constexpr int STEP = 32 * VEC;          // elements one warp-wide vector load covers
   constexpr int CHUNK = STEP * QBATCH;    // elements per batch
-  const int mode = p.act_mode;
-  const bool recip = (p.div_mode == ASQ_DIV_RECIPROCAL);
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  float scale = 0.f, inv_scale = 0.f;
+  float scale = given_scale;
   uint4 buf[QBATCH];
 
-  if (mode == ASQ_ACT_ROW_SCALE_GIVEN || mode == ASQ_ACT_PER_TENSOR_DYNAMIC) scale = given_scale;
-  if (mode == ASQ_ACT_PER_TOKEN) {
+  if (QM == QM_ROW_DIV && find_absmax) {  // per-token: the row's own absmax first
     float amax = 0.f;
     if (K <= CHUNK) {  // whole row lives in registers: one HBM read
 #pragma unroll
@@ -275,11 +310,10 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
 #pragma unroll
       for (int j = 0; j < QBATCH; ++j) amax = vec_absmax<T>(buf[j], amax);
       scale = token_scale<T>(amax, p);
-      inv_scale = safe_inverse(scale);
 #pragma unroll
       for (int j = 0; j < QBATCH; ++j) {
         const int c = lane * VEC + j * STEP;
-        if (c < K) quantize_vec<T, FP8>(buf[j], qrow + c, mode, recip, scale, inv_scale, p);
+        if (c < K) quantize_vec<T, FP8, QM>(buf[j], qrow + c, scale, p);
       }
       return scale;
     }
@@ -294,7 +328,6 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
     }
     scale = token_scale<T>(amax, p);
   }
-  inv_scale = safe_inverse(scale);
   for (int c0 = 0; c0 < K; c0 += CHUNK) {  // second pass of a long per-token row re-reads it from L2
 #pragma unroll
     for (int j = 0; j < QBATCH; ++j) {
@@ -304,22 +337,37 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
 #pragma unroll
     for (int j = 0; j < QBATCH; ++j) {
       const int c = c0 + lane * VEC + j * STEP;
-      if (c < K) quantize_vec<T, FP8>(buf[j], qrow + c, mode, recip, scale, inv_scale, p);
+      if (c < K) quantize_vec<T, FP8, QM>(buf[j], qrow + c, scale, p);
     }
   }
-  return scale;
+  return (QM == QM_ROW_DIV || QM == QM_TENSOR_DYN) ? scale : 0.f;
+}
+
+template <typename T, bool FP8>
+__device__ __forceinline__ float quantize_row_typed(const LinearParams& p, int row, int lane, float tensor_scale) {
+  const size_t off = static_cast<size_t>(row) * p.K;
+  const T* xrow = reinterpret_cast<const T*>(p.x) + off;
+  uint8_t* qrow = p.a_q + off;
+  switch (p.act_mode) {  // warp-uniform: one branch per row, straight-line code per vector
+    case ASQ_ACT_PER_TOKEN:
+      return quantize_row<T, FP8, QM_ROW_DIV>(xrow, qrow, p.K, lane, p, 0.f, true);
+    case ASQ_ACT_ROW_SCALE_GIVEN:
+      return quantize_row<T, FP8, QM_ROW_DIV>(xrow, qrow, p.K, lane, p, __ldg(p.row_scale_in + row), false);
+    case ASQ_ACT_PER_TENSOR_DYNAMIC:
+      return quantize_row<T, FP8, QM_TENSOR_DYN>(xrow, qrow, p.K, lane, p, tensor_scale, false);
+    case ASQ_ACT_SCALE:
+      return (p.div_mode == ASQ_DIV_RECIPROCAL) ? quantize_row<T, FP8, QM_SCALE_RECIP>(xrow, qrow, p.K, lane, p, 0.f, false)
+                                                : quantize_row<T, FP8, QM_SCALE_DIV>(xrow, qrow, p.K, lane, p, 0.f, false);
+    default:
+      return quantize_row<T, FP8, QM_ROUND>(xrow, qrow, p.K, lane, p, 0.f, false);
+  }
 }
 
 template <bool FP8>
 __device__ __forceinline__ float quantize_row_any(const LinearParams& p, int row, int lane, float tensor_scale = 0.f) {
-  uint8_t* qrow = p.a_q + static_cast<size_t>(row) * p.K;
-  const size_t off = static_cast<size_t>(row) * p.K;
-  const float given = (p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN) ? __ldg(p.row_scale_in + row) : tensor_scale;
-  if (p.x_dtype == ASQ_BF16)
-    return quantize_row<__nv_bfloat16, FP8>(reinterpret_cast<const __nv_bfloat16*>(p.x) + off, qrow, p.K, lane, p, given);
-  if (p.x_dtype == ASQ_F16)
-    return quantize_row<__half, FP8>(reinterpret_cast<const __half*>(p.x) + off, qrow, p.K, lane, p, given);
-  return quantize_row<float, FP8>(reinterpret_cast<const float*>(p.x) + off, qrow, p.K, lane, p, given);
+  if (p.x_dtype == ASQ_BF16) return quantize_row_typed<__nv_bfloat16, FP8>(p, row, lane, tensor_scale);
+  if (p.x_dtype == ASQ_F16) return quantize_row_typed<__half, FP8>(p, row, lane, tensor_scale);
+  return quantize_row_typed<float, FP8>(p, row, lane, tensor_scale);
 }
 
 // Per-tensor DYNAMIC scale (per_tensor_quantize_fp8, quantization.py:144-170): s = T(max|x|) / T(448) over the
@@ -363,15 +411,6 @@ __device__ __forceinline__ float tensor_scale_phase(const LinearParams& p, int f
 }
 
 // ------------------------------------------------------------------ epilogue
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
 __device__ __forceinline__ float load_bias_any(const void* b, int dtype, int col) {
   if (dtype == ASQ_I8) return static_cast<float>(reinterpret_cast<const int8_t*>(b)[col]);
   if (dtype == ASQ_I32) return static_cast<float>(reinterpret_cast<const int32_t*>(b)[col]);
@@ -471,8 +510,13 @@ __device__ __forceinline__ void epilogue_values(const uint32_t (&r)[32], float (
 
 // 32 fp32 results -> packed output words of the requested type (w[] holds 32 * elem_size / 4 words).
 __device__ __forceinline__ void pack_out16(const float (&v)[32], uint32_t (&w)[16], bool bf) {
+  if (bf) {  // one warp-uniform branch, not a select per element
 #pragma unroll
-  for (int j = 0; j < 16; ++j) w[j] = bf ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : pack_f16x2(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+  }
 }
 
 // EPI_SWIGLU: vg / vu = dequantised (fp32) gate and up values of the same 32 logical columns.  Follows the eager
@@ -481,19 +525,6 @@ __device__ __forceinline__ void pack_out16(const float (&v)[32], uint32_t (&w)[1
 // producer kernel emit identical bytes.  BF / OUT are compile-time so the 32 elements are straight-line code:
 // every rounding to T is a packed F2FP (two values per instruction) followed by a shift / mask unpack.
 //   OUT 0: w[16] = the product as T;  OUT 1: w[8] = int8, division as reciprocal multiply;  OUT 2: int8, IEEE division
-template <bool BF>
-__device__ __forceinline__ void round_pair(float& a, float& b) {
-  if (BF) {
-    const uint32_t w = pack_bf16x2(a, b);
-    a = __uint_as_float(w << 16);
-    b = __uint_as_float(w & 0xFFFF0000u);
-  } else {
-    uint32_t w = pack_f16x2(a, b);
-    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
-    a = f.x;
-    b = f.y;
-  }
-}
 template <bool BF, int OUT>
 __device__ __forceinline__ void swiglu_chunk(const float (&vg)[32], const float (&vu)[32], uint32_t* w, const LinearParams& p) {
   const float qs = p.out_quant_scale, inv = p.inv_out_quant_scale;
@@ -521,6 +552,67 @@ __device__ __forceinline__ void swiglu_chunk(const float (&vg)[32], const float 
     if (OUT != 0) w[j] = cvt_s8x4(t[0], t[1], t[2], t[3]);
   }
 }
+// RoPE on one 32-column chunk pair of a 128-wide head: va = columns d .. d+31 of the first half, vb = the same
+// columns of the second half (d + 64).  out[d] = T(T(x[d]*cos[d]) + T(rot[d]*sin[d])), rot = (-x2, x1), every
+// product rounded to T first — the arithmetic of asq_glue.cu's rope_kernel (HF apply_rotary_pos_emb in T).
+// Tables are BLOCKED [16][S][8]: entry (pos, col) lives at ((col / 8) * S + pos) * 8 + col % 8, so the 32 lanes of
+// a warp (32 consecutive positions) read 512 contiguous bytes per 16-byte load instead of 32 separate lines.
+// cosp / sinp point at block (d / 8) of this row's position; `blk` = S * 8 elements between blocks.
+template <bool BF>
+__device__ __forceinline__ void unpack_pair(uint32_t w, float& a, float& b) {
+  if (BF) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xFFFF0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    a = f.x;
+    b = f.y;
+  }
+}
+template <bool BF>
+__device__ __forceinline__ void rope_chunk(const float (&va)[32], const float (&vb)[32], uint32_t (&wa)[16], uint32_t (&wb)[16],
+                                           bool rot, const uint16_t* __restrict__ cosp, const uint16_t* __restrict__ sinp,
+                                           size_t blk, bool halves_equal) {
+  if (!rot) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      wa[j] = BF ? pack_bf16x2(va[2 * j], va[2 * j + 1]) : pack_f16x2(va[2 * j], va[2 * j + 1]);
+      wb[j] = BF ? pack_bf16x2(vb[2 * j], vb[2 * j + 1]) : pack_f16x2(vb[2 * j], vb[2 * j + 1]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 ca = __ldg(reinterpret_cast<const uint4*>(cosp + q * blk)), sa = __ldg(reinterpret_cast<const uint4*>(sinp + q * blk));
+    // HF tables repeat their first half (emb = cat(freqs, freqs)); the caller vouches for it to halve the table reads
+    const uint4 cb = halves_equal ? ca : __ldg(reinterpret_cast<const uint4*>(cosp + (8 + q) * blk));
+    const uint4 sb = halves_equal ? sa : __ldg(reinterpret_cast<const uint4*>(sinp + (8 + q) * blk));
+    const uint32_t caw[4] = {ca.x, ca.y, ca.z, ca.w}, saw[4] = {sa.x, sa.y, sa.z, sa.w};
+    const uint32_t cbw[4] = {cb.x, cb.y, cb.z, cb.w}, sbw[4] = {sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x0 = va[8 * q + 2 * i], x1 = va[8 * q + 2 * i + 1], y0 = vb[8 * q + 2 * i], y1 = vb[8 * q + 2 * i + 1];
+      round_pair<BF>(x0, x1);  // the projection's output in T
+      round_pair<BF>(y0, y1);
+      float c0, c1, s0, s1;
+      unpack_pair<BF>(caw[i], c0, c1);
+      unpack_pair<BF>(saw[i], s0, s1);
+      float p0 = __fmul_rn(x0, c0), p1 = __fmul_rn(x1, c1), q0 = __fmul_rn(-y0, s0), q1 = __fmul_rn(-y1, s1);
+      round_pair<BF>(p0, p1);
+      round_pair<BF>(q0, q1);
+      const float oa0 = __fadd_rn(p0, q0), oa1 = __fadd_rn(p1, q1);
+      wa[4 * q + i] = BF ? pack_bf16x2(oa0, oa1) : pack_f16x2(oa0, oa1);
+      unpack_pair<BF>(cbw[i], c0, c1);
+      unpack_pair<BF>(sbw[i], s0, s1);
+      p0 = __fmul_rn(y0, c0); p1 = __fmul_rn(y1, c1); q0 = __fmul_rn(x0, s0); q1 = __fmul_rn(x1, s1);
+      round_pair<BF>(p0, p1);
+      round_pair<BF>(q0, q1);
+      const float ob0 = __fadd_rn(p0, q0), ob1 = __fadd_rn(p1, q1);
+      wb[4 * q + i] = BF ? pack_bf16x2(ob0, ob1) : pack_f16x2(ob0, ob1);
+    }
+  }
+}
+
 __device__ __forceinline__ void swiglu_dispatch(const float (&vg)[32], const float (&vu)[32], uint32_t* w, const LinearParams& p) {
   const bool bf = (p.mid_dtype == ASQ_BF16);
   if (p.y_dtype != ASQ_I8) {
@@ -999,6 +1091,56 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
+      if (p.rope_cos != nullptr) {
+        // Fused q|k|v projection with RoPE: this warp takes groups 2*half and 2*half+1 = one whole 128-wide
+        // head of its 32 rows, so both operands of the rotation (columns d and d + 64) are in its registers.
+        // Both staging buffers are used per tile (one per 64-column group), then two TMA stores.
+        const int g0 = 2 * half;
+        if (g0 < ngroups) {
+          if (gcount > 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          const uint32_t buf_a = stage_base, buf_b = stage_base + EPI_BUF_BYTES;
+          const int colh = tile_col0 + g0 * UNIT_N;
+          const bool rot = colh < p.rope_cols;
+          const bool bf = (p.y_dtype == ASQ_BF16);
+          const size_t blk = static_cast<size_t>(p.rope_S) * 8;  // elements between 8-column table blocks
+          const size_t tab = static_cast<size_t>(row % p.rope_S) * 8;
+          const uint16_t* cos_row = reinterpret_cast<const uint16_t*>(p.rope_cos) + tab;
+          const uint16_t* sin_row = reinterpret_cast<const uint16_t*>(p.rope_sin) + tab;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(taddr0 + g0 * UNIT_N + c * 32, ra);
+            tmem_ld_32x32(taddr0 + g0 * UNIT_N + UNIT_N + c * 32, rb);
+            tmem_ld_wait();
+            float va[32], vb[32];
+            epilogue_values<FP8>(ra, va, colh + c * 32, rs, p);
+            epilogue_values<FP8>(rb, vb, colh + UNIT_N + c * 32, rs, p);
+            uint32_t wa[16], wb[16];
+            if (bf) rope_chunk<true>(va, vb, wa, wb, rot, cos_row + c * 4 * blk, sin_row + c * 4 * blk, blk, p.rope_halves_equal != 0);
+            else    rope_chunk<false>(va, vb, wa, wb, rot, cos_row + c * 4 * blk, sin_row + c * 4 * blk, blk, p.rope_halves_equal != 0);
+            stage_words<16>(buf_a, lane, c * 4, wa);
+            stage_words<16>(buf_b, lane, c * 4, wb);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tma_store_2d(&tmY, buf_a, colh * elem, row0);
+            if (colh + UNIT_N < p.N) tma_store_2d(&tmY, buf_b, (colh + UNIT_N) * elem, row0);
+            tma_store_commit();
+          }
+          gcount += 2;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+          else         mbar_arrive(tempty_bar(acc));
+        }
+        continue;
+      }
       int chunk_pair = 0;  // index of the (r0, r1) pair inside this warp's stream-K region
 #pragma unroll 1
       for (int g = half; g < ngroups; g += 2, ++chunk_pair) {
@@ -1439,7 +1581,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     static int mc_env = -1;
     if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     const int want = mc_env ? mc_env : 1;
-    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU) {
+    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr) {
       const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
       const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
       if (clusters > 0 && super_tiles >= clusters) mc = 2;
@@ -1459,7 +1601,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (tu_env < 0) { const char* e = getenv("ASQ_TILE_UNITS"); tu_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     if (mc == 2) {
       p.tile_units = 2 * asq::TILE_N / asq::UNIT_N;  // the walk hands out 512-wide super tiles, one half per pair
-    } else if (tu_env) {
+    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr) {
       p.tile_units = tu_env;
     } else {
       // Wave quantisation: pick 256- or 192-column tiles, whichever needs less (rounds x width); 192-wide tiles
@@ -1657,6 +1799,32 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
   const float ds = (act_mode == ASQ_ACT_SCALE) ? w_scale * in_scale : w_scale;
   return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, in_scale, ds, nullptr,
                       row_scale_out, div_mode, workspace, workspace_bytes, stream, out_scale);
+}
+
+int asq_w8a8_linear_q8_rope(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,
+                            int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                            const void* cos_table, const void* sin_table, int64_t S, int64_t rope_cols, int64_t head_dim,
+                            int halves_equal, void* stream) {
+  int rc = check_common(xq, w, y, M, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (y_dtype != ASQ_BF16 && y_dtype != ASQ_F16) return fail(ASQ_ERR_INVALID, "rope epilogue: y dtype must be f16 or bf16");
+  if (head_dim != 128) return fail(ASQ_ERR_UNSUPPORTED, "rope epilogue: head_dim %lld (only 128; use asq_rope_inplace)", (long long)head_dim);
+  if (N % 128 != 0 || rope_cols % 128 != 0 || rope_cols < 0 || rope_cols > N)
+    return fail(ASQ_ERR_INVALID, "rope epilogue: N=%lld and rope_cols=%lld must be multiples of 128, rope_cols <= N", (long long)N, (long long)rope_cols);
+  if (S <= 0 || S > 0x7fffffffLL) return fail(ASQ_ERR_INVALID, "rope epilogue: bad table length S=%lld", (long long)S);
+  if (M == 0) return ASQ_OK;
+  if (cos_table == nullptr || sin_table == nullptr || (reinterpret_cast<uintptr_t>(cos_table) & 15) || (reinterpret_cast<uintptr_t>(sin_table) & 15))
+    return fail(ASQ_ERR_INVALID, "rope epilogue: cos / sin tables must be non-null and 16-byte aligned");
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT;
+  p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
+  p.row_scale = const_cast<float*>(row_scale);
+  p.rope_cos = cos_table; p.rope_sin = sin_table; p.rope_S = static_cast<int>(S); p.rope_cols = static_cast<int>(rope_cols);
+  p.rope_halves_equal = halves_equal ? 1 : 0;
+  return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream));
 }
 
 int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,

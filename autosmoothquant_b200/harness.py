@@ -14,6 +14,7 @@ Weights are synthetic (seeded normal, true shapes), converted with the modules' 
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -213,6 +214,28 @@ class QuantDecoderLayer(nn.Module):
         return x
 
 
+_BLOCKED_ROPE = {}
+
+
+def _blocked_rope(cos: torch.Tensor, sin: torch.Tensor):
+    """The RoPE epilogue's blocked copies of the tables (built once per table pair)."""
+    from . import _lib
+
+    key = (cos.data_ptr(), sin.data_ptr(), tuple(cos.shape), cos.dtype)
+    hit = _BLOCKED_ROPE.get(key)
+    if hit is None:
+        _BLOCKED_ROPE.clear()
+        half = cos.shape[1] // 2
+        dup = bool(torch.equal(cos[:, :half], cos[:, half:]) and torch.equal(sin[:, :half], sin[:, half:]))
+        hit = _BLOCKED_ROPE[key] = (_lib.rope_tables_blocked(cos), _lib.rope_tables_blocked(sin), dup)
+    return hit
+
+
+def _rope_arg(cos, sin, S, rope_cols):
+    c, s, dup = _blocked_rope(cos, sin)
+    return (c, s, S, rope_cols, dup)
+
+
 def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Optional[torch.Tensor], B: int, S: int,
                         cos: torch.Tensor, sin: torch.Tensor):
     """One decoder layer with the producer-side fusions of asq_glue.cu (per-tensor INT8, fused projections):
@@ -225,10 +248,13 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     hd = cfg.head_dim
     x2, _, q8 = _lib.add_rmsnorm_quant(x2, delta, layer.input_layernorm_weight, cfg.rms_eps)
     qkv_mod = layer.qkv_proj
-    qkv = _lib.w8a8_linear_q8(q8, qkv_mod.weight, qkv_mod.bias if qkv_mod.use_bias else None, 1.0,
-                              col_scale=qkv_mod._col_scale(x2.device), out_dtype=x2.dtype)
     nq, nk, nv = (n // hd for n in layer.qkv_sizes)
-    _lib.rope_inplace(qkv, cos, sin, S, nq + nk, hd)
+    rope_in_epilogue = hd == 128 and os.environ.get("ASQ_ROPE_EPILOGUE", "1") != "0"
+    qkv = _lib.w8a8_linear_q8(q8, qkv_mod.weight, qkv_mod.bias if qkv_mod.use_bias else None, 1.0,
+                              col_scale=qkv_mod._col_scale(x2.device), out_dtype=x2.dtype,
+                              rope=_rope_arg(cos, sin, S, (nq + nk) * hd) if rope_in_epilogue else None)
+    if not rope_in_epilogue:
+        _lib.rope_inplace(qkv, cos, sin, S, nq + nk, hd)
     q, k, v = qkv.split(layer.qkv_sizes, dim=-1)
     q = q.view(B, S, nq, hd).transpose(1, 2)
     k = k.view(B, S, nk, hd).transpose(1, 2)
@@ -236,7 +262,14 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=nk != nq)
     # o_proj: the module quantises the attention output in-kernel; under tensor parallelism it is the
     # row-parallel wrapper, whose forward ends with the all-reduce
-    o = layer.o_proj(attn.transpose(1, 2).reshape(B * S, nq * hd))
+    attn2 = attn.transpose(1, 2).reshape(B * S, nq * hd)
+    if os.environ.get("ASQ_OPROJ_SPLIT") == "1" and getattr(layer, "tp_world", 1) == 1:
+        om = layer.o_proj
+        q8o, _ = _lib.quantize_act(attn2, _lib.ACT_SCALE, float(om.quant_scale.item()))
+        o = _lib.w8a8_linear_q8(q8o, om.weight, om.bias if om.use_bias else None, float(om.dequant_scale.item()),
+                                out_dtype=x2.dtype)
+    else:
+        o = layer.o_proj(attn2)
     x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
     tp_world = getattr(layer, "tp_world", 1)
     down = layer.down_proj.shard if tp_world > 1 else layer.down_proj

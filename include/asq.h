@@ -148,6 +148,20 @@ int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w
                        float dequant_scale, const float* col_scale,
                        void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
+/* asq_w8a8_linear_q8 for the fused q|k|v projection with HF rotate-half RoPE applied in the epilogue (what
+ * asq_rope_inplace does as a second pass over the same tensor): columns [0, rope_cols) — the q and k heads —
+ * are rotated per head, position = row % S; the remaining columns (v) are plain dequantised outputs.
+ * head_dim must be 128, N and rope_cols multiples of 128, y_dtype F16 | BF16.  The tables hold the HF
+ * [S, head_dim] cos / sin values in y's dtype, re-laid-out in 8-column blocks as [head_dim/8][S][8] (entry
+ * (pos, col) at ((col/8)*S + pos)*8 + col%8) so that the 32 rows a warp owns read contiguous memory.
+ * halves_equal != 0: the caller guarantees table[:, d] == table[:, d + head_dim/2] (true for HF's
+ * emb = cat(freqs, freqs)), and only the first half is read. */
+int asq_w8a8_linear_q8_rope(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
+                            void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                            float dequant_scale, const float* col_scale,
+                            const void* cos_table, const void* sin_table, int64_t S, int64_t rope_cols,
+                            int64_t head_dim, int halves_equal, void* stream);
+
 /* gate|up projection with the SwiGLU product (and the next Linear's activation quantisation) in the GEMM
  * epilogue: the [M, 2I] gate|up tensor of HF LlamaMLP.forward (borrowed at models/llama.py:218) never
  * reaches HBM.  Replaces asq_w8a8_linear_q8 (fused gate|up) + asq_silu_mul_quant byte for byte.

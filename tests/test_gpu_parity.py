@@ -467,6 +467,48 @@ def test_gateup_swiglu_epilogue_equals_two_launch_path(dtype, M, I, K, per_token
     assert torch.equal(q3, L.silu_mul_quant(gu3, qs, div_mode=mode)[0])
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,S,nq,nk,nv,K,per_token,bias", [(300, 150, 3, 1, 1, 512, False, True), (64, 64, 2, 2, 2, 256, True, False),
+                                                           (2048, 2048, 32, 32, 32, 4096, False, False)])
+def test_rope_epilogue_equals_gemm_then_rope_kernel(dtype, M, S, nq, nk, nv, K, per_token, bias):
+    """RoPE in the q|k|v GEMM epilogue == the GEMM followed by asq_rope_inplace (itself bit-exact against the
+    oracle's HF rotate-half, test_rope_inplace_bit_exact); v columns must be untouched."""
+    if M == 2048 and dtype == "f16":
+        pytest.skip("full-size case runs once")
+    hd = 128
+    g = torch.Generator().manual_seed(M + nq)
+    td = TORCH_DT[dtype]
+    N = (nq + nk + nv) * hd
+    xq = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(DEV)
+    w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(DEV)
+    sc = 3e-6 * (4096 / K) ** 0.5
+    cs = torch.cat([torch.full((nq * hd,), sc), torch.full((nk * hd,), 1.3 * sc), torch.full((nv * hd,), 0.7 * sc)]).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV) if bias else None
+    rs = (torch.rand(M, generator=g) + 0.5).to(DEV) if per_token else None
+    ang = torch.outer(torch.arange(S, dtype=torch.float32), 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd)))
+    emb = torch.cat([ang, ang], dim=-1)
+    cos, sin = emb.cos().to(td).to(DEV), emb.sin().to(td).to(DEV)
+    want = L.w8a8_linear_q8(xq, w, b, 1.0, col_scale=cs, row_scale=rs, out_dtype=td)
+    plain = want.clone()
+    L.rope_inplace(want, cos, sin, S, nq + nk, hd)
+    got = L.w8a8_linear_q8(xq, w, b, 1.0, col_scale=cs, row_scale=rs, out_dtype=td, rope=(L.rope_tables_blocked(cos), L.rope_tables_blocked(sin), S, (nq + nk) * hd))
+    torch.cuda.synchronize()
+    assert not torch.equal(want, plain)  # the rotation did something
+    assert torch.equal(got[:, (nq + nk) * hd:], plain[:, (nq + nk) * hd:])
+    assert torch.equal(got, want), f"{(got != want).sum().item()} elements differ"
+    got2 = L.w8a8_linear_q8(xq, w, b, 1.0, col_scale=cs, row_scale=rs, out_dtype=td,
+                            rope=(L.rope_tables_blocked(cos), L.rope_tables_blocked(sin), S, (nq + nk) * hd, True))
+    assert torch.equal(got2, want)  # HF tables repeat their first half: the halves_equal fast path is identical
+
+
+def test_rope_epilogue_rejects_unsupported_head_dim():
+    xq = torch.zeros((4, 64), dtype=torch.int8, device=DEV)
+    w = torch.zeros((128, 64), dtype=torch.int8, device=DEV)
+    t64 = L.rope_tables_blocked(torch.zeros((8, 64), dtype=torch.bfloat16, device=DEV))
+    with pytest.raises(RuntimeError, match="head_dim"):
+        L.w8a8_linear_q8(xq, w, None, 1.0, rope=(t64, t64, 8, 128))
+
+
 def test_gateup_swiglu_rejects_bad_arguments():
     xq = torch.zeros((4, 64), dtype=torch.int8, device=DEV)
     w = torch.zeros((96, 64), dtype=torch.int8, device=DEV)  # N = 96 is not a multiple of 64
