@@ -46,6 +46,13 @@ EXPORTED_SYMBOLS = (
     "asq_w8a8_linear_q8",
     "asq_w8a8_gateup_swiglu_q8",
     "asq_w8a8_linear_q8_rope",
+    "asq_ar_buffer_bytes",
+    "asq_w8a8_linear_q8_allreduce",
+    "asq_dev_alloc",
+    "asq_dev_free",
+    "asq_ipc_export",
+    "asq_ipc_open",
+    "asq_ipc_close",
     "asq_add_rmsnorm_quant",
     "asq_silu_mul_quant",
     "asq_rope_inplace",
@@ -121,6 +128,22 @@ def load():
         lib.asq_w8a8_linear_q8_rope.restype = c_i
         lib.asq_w8a8_linear_q8_rope.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
                                                 c_vp, c_vp, c_i64, c_i64, c_i64, c_i, c_vp]
+        c_pp = ctypes.POINTER(ctypes.c_void_p)
+        lib.asq_ar_buffer_bytes.restype = c_i
+        lib.asq_ar_buffer_bytes.argtypes = [c_i64, c_i64, c_i, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]
+        lib.asq_w8a8_linear_q8_allreduce.restype = c_i
+        lib.asq_w8a8_linear_q8_allreduce.argtypes = [c_vp, c_vp, c_vp, c_vp, c_pp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
+                                                     c_pp, c_pp, c_i, c_i, c_vp]
+        lib.asq_dev_alloc.restype = c_i
+        lib.asq_dev_alloc.argtypes = [c_sz, c_pp]
+        lib.asq_dev_free.restype = c_i
+        lib.asq_dev_free.argtypes = [c_vp]
+        lib.asq_ipc_export.restype = c_i
+        lib.asq_ipc_export.argtypes = [c_vp, c_vp]
+        lib.asq_ipc_open.restype = c_i
+        lib.asq_ipc_open.argtypes = [c_vp, c_pp]
+        lib.asq_ipc_close.restype = c_i
+        lib.asq_ipc_close.argtypes = [c_vp]
         lib.asq_add_rmsnorm_quant.restype = c_i
         lib.asq_add_rmsnorm_quant.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_f, c_vp]
         lib.asq_silu_mul_quant.restype = c_i

@@ -93,6 +93,17 @@ struct LinearParams {
   int sk_enabled, sk_total, sk_workers;  // sk_workers <= launched workers: every participant gets >= 1 iteration
   uint32_t* sk_partial;
   uint32_t* sk_flags;
+  // Row-parallel GEMM fused with its all-reduce over peer memory (NVLink P2P): every rank computes the partial
+  // of every tile over its K shard; tile t is OWNED by rank t % world.  Non-owners push their raw int32 / fp32
+  // accumulators into the owner's receive buffer and raise a flag; the owner adds them to its own accumulator
+  // (exact for int32, rank order for fp32), runs the normal epilogue and TMA-stores the finished tile into the
+  // y buffer of EVERY rank.  Each rank walks the tiles it does not own first, so partials arrive before their
+  // owner needs them.  ar_ctl[r] / ar_recv[r] are rank r's control words and receive buffer mapped into this
+  // process; words: [0] epoch of the last finished launch, [1] CTAs finished, [2+s] "rank s finished launch e",
+  // [64...] one arrival flag per (source slot, owned tile, CTA of the pair, epilogue warp).
+  int ar_world, ar_rank, ar_tiles, ar_cnt_max;
+  uint32_t* ar_ctl[8];
+  uint32_t* ar_recv[8];
   int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
   unsigned long long* dbg;  // optional timeline buffer (8 slots per CTA), nullptr in production
 };
@@ -736,8 +747,9 @@ struct Seg {
   int kb0, kb1;            // k-block range [kb0, kb1) this worker accumulates
   int role;                // SEG_COMPLETE: whole K, normal epilogue; SEG_CONTRIB: writes a partial; SEG_OWNER: adds partials
   int tile_g0;             // owner: first stream-K iteration index of its tile
+  int ar_tile;             // all-reduce mode: linear tile id (owner = ar_tile % world, slot = ar_tile / world)
 };
-enum : int { SEG_COMPLETE = 0, SEG_CONTRIB = 1, SEG_OWNER = 2 };
+enum : int { SEG_COMPLETE = 0, SEG_CONTRIB = 1, SEG_OWNER = 2, SEG_AR_CONTRIB = 3, SEG_AR_OWNER = 4 };
 
 struct TileWalk {
   const LinearParams& p;
@@ -756,6 +768,19 @@ struct TileWalk {
   }
   __device__ void set_tile(Seg& sg, int t) const {
     int n_blk;
+    if (p.ar_world > 1) {
+      // walk order of this rank: the tiles owned by rank+1, rank+2, ... first, its own tiles last
+      int i = t, owner = p.ar_rank;
+      for (int s = 1; s <= p.ar_world; ++s) {
+        owner = (p.ar_rank + s) % p.ar_world;
+        const int cnt = (p.ar_tiles - owner + p.ar_world - 1) / p.ar_world;
+        if (i < cnt) break;
+        i -= cnt;
+      }
+      t = owner + p.ar_world * i;
+      sg.ar_tile = t;
+      sg.role = (owner == p.ar_rank) ? SEG_AR_OWNER : SEG_AR_CONTRIB;
+    }
     tile_coords(t, p, sg.m_blk, n_blk);
     const int U = p.tile_units;  // tile width in 64-column units: 4, or fewer for decode-sized problems
     sg.col0 = n_blk * U * UNIT_N;
@@ -806,6 +831,26 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// All-reduce scratch addressing on rank `dst` (its receive buffer / flag words as mapped into this process).
+// `slot` = (source - dst - 1 + world) % world numbers the world-1 possible sources of a destination.
+constexpr int AR_FLAG_BASE = 64;
+__device__ __forceinline__ size_t ar_index(const LinearParams& p, int slot, int owned_idx, int cg, uint32_t cta_rank, int ew) {
+  return ((static_cast<size_t>(slot) * p.ar_cnt_max + owned_idx) * cg + cta_rank) * NUM_EPI_WARPS + ew;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+struct PeerMaps {
+  CUtensorMap m[7];  // output maps of the other ranks' y buffers (all-reduce mode), in rank order skipping self
+};
+
 // ------------------------------------------------------------------ the kernel
 // MC = CTA pairs per cluster (1 or 2).  With MC == 2 a cluster of four CTAs owns a 256-row x 512-column
 // super tile: pair p computes columns [p*256, p*256+256), both pairs need the same activation rows, so every
@@ -815,7 +860,7 @@ template <bool FP8, int CG, int MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmBu, const __grid_constant__ CUtensorMap tmY,
-                  const LinearParams p) {
+                  const __grid_constant__ PeerMaps tmPeers, const LinearParams p) {
   using Cfg = TileCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -1012,6 +1057,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC) &&
                                (p.epi_kind == EPI_DEQUANT || p.epi_kind == EPI_SWIGLU);
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
+    // all-reduce mode: this launch's epoch = 1 + the epoch of the last launch that finished on this rank
+    const uint32_t ar_epoch = (p.ar_world > 1) ? __ldcg(p.ar_ctl[p.ar_rank]) + 1u : 0u;
     int it = 0;
     TileWalk walk(p, worker, num_workers);
     Seg sg;
@@ -1036,6 +1083,15 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int c = 0; c < n_contrib; ++c) {
             const uint32_t* f = sk_flag(p, worker + 1 + c, CG, cta_rank, ew);
             while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
+          }
+        }
+        __syncwarp();
+      }
+      if (sg.role == SEG_AR_OWNER) {  // the other ranks' partials of this tile must have landed in our buffer
+        if (lane == 0) {
+          for (int sl = 0; sl < p.ar_world - 1; ++sl) {
+            const uint32_t* f = p.ar_ctl[p.ar_rank] + AR_FLAG_BASE + ar_index(p, sl, sg.ar_tile / p.ar_world, CG, cta_rank, ew);
+            while (ld_acquire_sys(f) != ar_epoch) __nanosleep(100);
           }
         }
         __syncwarp();
@@ -1159,6 +1215,44 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 8; ++q) __stcg(dst + (8 + q) * 32, make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]));
           continue;
         }
+        if (sg.role == SEG_AR_CONTRIB) {
+          // raw partial accumulators -> the owner's receive buffer over NVLink, coalesced 512-byte warp stores
+          tmem_ld_wait();
+          const int owner = sg.ar_tile % p.ar_world;
+          const int slot = (p.ar_rank - owner - 1 + p.ar_world) % p.ar_world;
+          uint4* dst = reinterpret_cast<uint4*>(p.ar_recv[owner] + ar_index(p, slot, sg.ar_tile / p.ar_world, CG, cta_rank, ew) * SK_WARP_WORDS) +
+                       chunk_pair * 2 * 8 * 32 + lane;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q * 32] = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[(8 + q) * 32] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
+          continue;
+        }
+        if (sg.role == SEG_AR_OWNER) {
+          tmem_ld_wait();
+          for (int sl = 0; sl < p.ar_world - 1; ++sl) {  // fixed source order: deterministic fp32 sums
+            const uint4* src = reinterpret_cast<const uint4*>(p.ar_recv[p.ar_rank] + ar_index(p, sl, sg.ar_tile / p.ar_world, CG, cta_rank, ew) * SK_WARP_WORDS) +
+                               chunk_pair * 2 * 8 * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 a = __ldcg(src + q * 32);
+              const uint4 b = __ldcg(src + (8 + q) * 32);
+              if (FP8) {
+                r0[4 * q] = __float_as_uint(__uint_as_float(r0[4 * q]) + __uint_as_float(a.x));
+                r0[4 * q + 1] = __float_as_uint(__uint_as_float(r0[4 * q + 1]) + __uint_as_float(a.y));
+                r0[4 * q + 2] = __float_as_uint(__uint_as_float(r0[4 * q + 2]) + __uint_as_float(a.z));
+                r0[4 * q + 3] = __float_as_uint(__uint_as_float(r0[4 * q + 3]) + __uint_as_float(a.w));
+                r1[4 * q] = __float_as_uint(__uint_as_float(r1[4 * q]) + __uint_as_float(b.x));
+                r1[4 * q + 1] = __float_as_uint(__uint_as_float(r1[4 * q + 1]) + __uint_as_float(b.y));
+                r1[4 * q + 2] = __float_as_uint(__uint_as_float(r1[4 * q + 2]) + __uint_as_float(b.z));
+                r1[4 * q + 3] = __float_as_uint(__uint_as_float(r1[4 * q + 3]) + __uint_as_float(b.w));
+              } else {  // int32 partial sums: exact, so the result equals the unsharded GEMM bit for bit
+                r0[4 * q] += a.x; r0[4 * q + 1] += a.y; r0[4 * q + 2] += a.z; r0[4 * q + 3] += a.w;
+                r1[4 * q] += b.x; r1[4 * q + 1] += b.y; r1[4 * q + 2] += b.z; r1[4 * q + 3] += b.w;
+              }
+            }
+          }
+        }
         if (sg.role == SEG_OWNER) {
           tmem_ld_wait();
           for (int c = 0; c < n_contrib; ++c) {
@@ -1203,6 +1297,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (lane == 0 && row0 < p.M && col0 < p.N) {
             tma_store_2d(&tmY, buf, col0 * elem, row0);
+            for (int pr = 0; pr < p.ar_world - 1; ++pr) tma_store_2d(&tmPeers.m[pr], buf, col0 * elem, row0);  // all-gather by stores
             tma_store_commit();
           }
           ++gcount;
@@ -1248,6 +1343,12 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (CG == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
         else         mbar_arrive(tempty_bar(acc));
         if (sg.role == SEG_CONTRIB) st_release_gpu(sk_flag(p, worker, CG, cta_rank, ew), 1u);  // partial published
+        if (sg.role == SEG_AR_CONTRIB) {  // __syncwarp above ordered the other lanes' stores before this fence
+          const int owner = sg.ar_tile % p.ar_world;
+          const int slot = (p.ar_rank - owner - 1 + p.ar_world) % p.ar_world;
+          fence_acq_rel_sys();
+          st_release_sys(p.ar_ctl[owner] + AR_FLAG_BASE + ar_index(p, slot, sg.ar_tile / p.ar_world, CG, cta_rank, ew), ar_epoch);
+        }
         if (sg.role == SEG_OWNER)
           for (int c = 0; c < n_contrib; ++c) *sk_flag(p, worker + 1 + c, CG, cta_rank, ew) = 0u;  // consumed: re-arm
       }
@@ -1263,6 +1364,26 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (threadIdx.x == 0) ASQ_STAMP(7);
+  if (p.ar_world > 1 && threadIdx.x == 0) {
+    // This CTA's tiles are stored everywhere (each epilogue warp waited for its TMA stores before the sync above).
+    // The last CTA of the rank tells every peer "rank r finished launch e", waits for the same word from every
+    // peer (their stores into OUR y and their reads of OUR partials are then complete) and advances the epoch.
+    uint32_t* ctl = p.ar_ctl[p.ar_rank];
+    const uint32_t epoch = __ldcg(ctl) + 1u;
+    __threadfence_system();
+    const uint32_t done = atomicAdd(ctl + 1, 1u);
+    if (done == gridDim.x - 1) {
+      ctl[1] = 0u;
+      __threadfence_system();
+      for (int r = 0; r < p.ar_world; ++r)
+        if (r != p.ar_rank) st_release_sys(p.ar_ctl[r] + 2 + p.ar_rank, epoch);
+      for (int r = 0; r < p.ar_world; ++r)
+        if (r != p.ar_rank)
+          while (ld_acquire_sys(ctl + 2 + r) != epoch) __nanosleep(200);
+      ctl[0] = epoch;
+      __threadfence_system();
+    }
+  }
   if (fused && threadIdx.x == 0) {
     // last CTA out restores the phase counters so the workspace is reusable by the next launch
     __threadfence();
@@ -1435,7 +1556,7 @@ constexpr int kMaxDevices = 64;
 
 template <bool FP8, int CG, int MC>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBu, const CUtensorMap& tmY,
-               const asq::LinearParams& p, int workers, cudaStream_t stream) {
+               const asq::PeerMaps& tmPeers, const asq::LinearParams& p, int workers, cudaStream_t stream) {
   using Cfg = asq::TileCfg<CG>;
   auto kern = asq::asq_linear_kernel<FP8, CG, MC>;
   cudaError_t e;
@@ -1462,7 +1583,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBu, tmY, p);
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBu, tmY, tmPeers, p);
   if (e != cudaSuccess) return asq_glue_fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
 }
@@ -1507,7 +1628,8 @@ int max_multicast_clusters(int dev) {
 #endif
 #define ASQ_LAUNCH_INST(FP8, CG, MC)                                                                            \
   ASQ_LAUNCH_DECL int launch_cfg<FP8, CG, MC>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,        \
-                                              const CUtensorMap&, const asq::LinearParams&, int, cudaStream_t);
+                                              const CUtensorMap&, const asq::PeerMaps&, const asq::LinearParams&, \
+                                              int, cudaStream_t);
 #if ASQ_TU == 0 || ASQ_TU == 1
 ASQ_LAUNCH_INST(false, 1, 1)
 #endif
@@ -1561,7 +1683,8 @@ int attach_streamk(asq::LinearParams& p, void* workspace, size_t workspace_bytes
 }
 
 // Shared launcher: `a8` is the 8-bit A matrix TMA reads (caller's matrix, or the workspace copy).
-int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p, cudaStream_t stream) {
+int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p, cudaStream_t stream,
+                  void* const* peer_y = nullptr) {
   int dev;
   DeviceState* st;
   int rc = get_device(&dev, &st);
@@ -1581,7 +1704,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     static int mc_env = -1;
     if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     const int want = mc_env ? mc_env : 1;
-    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr) {
+    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1) {
       const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
       const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
       if (clusters > 0 && super_tiles >= clusters) mc = 2;
@@ -1601,7 +1724,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (tu_env < 0) { const char* e = getenv("ASQ_TILE_UNITS"); tu_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     if (mc == 2) {
       p.tile_units = 2 * asq::TILE_N / asq::UNIT_N;  // the walk hands out 512-wide super tiles, one half per pair
-    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr) {
+    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1) {
       p.tile_units = tu_env;
     } else {
       // Wave quantisation: pick 256- or 192-column tiles, whichever needs less (rounds x width); 192-wide tiles
@@ -1700,12 +1823,24 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       tmY = tmA;  // unused, but must be a valid descriptor
     }
   }
-  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2>(tmA, tmB, tmBu, tmY, p, workers, stream)
-                          : launch_cfg<false, 2, 2>(tmA, tmB, tmBu, tmY, p, workers, stream);
-  if (fp8) return cg == 2 ? launch_cfg<true, 2, 1>(tmA, tmB, tmBu, tmY, p, workers, stream)
-                          : launch_cfg<true, 1, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
-  return cg == 2 ? launch_cfg<false, 2, 1>(tmA, tmB, tmBu, tmY, p, workers, stream)
-                 : launch_cfg<false, 1, 1>(tmA, tmB, tmBu, tmY, p, workers, stream);
+  asq::PeerMaps tmPeers;
+  memset(&tmPeers, 0, sizeof(tmPeers));
+  if (p.ar_world > 1) {
+    if (!p.tma_store || peer_y == nullptr) return fail(ASQ_ERR_INVALID, "all-reduce mode needs a 16-byte aligned 16-bit output row pitch");
+    const long long row_bytes = static_cast<long long>(p.N) * 2;
+    for (int i = 0; i < p.ar_world - 1; ++i) {
+      rc = make_tmap(&tmPeers.m[i], peer_y[i], p.M, row_bytes, 32);
+      if (rc != ASQ_OK) return rc;
+    }
+    p.ar_tiles = p.num_m_blocks * p.num_n_blocks;
+    p.ar_cnt_max = (p.ar_tiles + p.ar_world - 1) / p.ar_world;
+  }
+  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
+                          : launch_cfg<false, 2, 2>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
+  if (fp8) return cg == 2 ? launch_cfg<true, 2, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
+                          : launch_cfg<true, 1, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
+  return cg == 2 ? launch_cfg<false, 2, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
+                 : launch_cfg<false, 1, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
 }
 
 int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {
@@ -1868,6 +2003,90 @@ int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const in
   p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
   p.row_scale = const_cast<float*>(row_scale);
   return launch_linear(false, xq, w_il, p, static_cast<cudaStream_t>(stream));
+}
+
+// ---- row-parallel GEMM fused with its all-reduce over peer memory
+int asq_ar_buffer_bytes(int64_t M, int64_t N, int world, size_t* recv_bytes, size_t* ctl_bytes) {
+  if (M <= 0 || N <= 0 || world < 2 || world > 8 || recv_bytes == nullptr || ctl_bytes == nullptr)
+    return fail(ASQ_ERR_INVALID, "asq_ar_buffer_bytes: bad arguments (world must be 2..8)");
+  // per tile one 128-row x 256-column 4-byte slot per CTA; pairs own 256-row tiles, so the total is the same
+  const int cg = pick_cta_group(M);
+  const int64_t tiles = ((M + asq::BLOCK_M * cg - 1) / (asq::BLOCK_M * cg)) * ((N + asq::TILE_N - 1) / asq::TILE_N);
+  const int64_t cnt_max = (tiles + world - 1) / world;
+  const int64_t slots = static_cast<int64_t>(world - 1) * cnt_max * cg;  // CTA slots
+  *recv_bytes = static_cast<size_t>(slots) * asq::SK_SLOT_WORDS * 4;
+  *ctl_bytes = round_up((asq::AR_FLAG_BASE + static_cast<size_t>(slots) * asq::NUM_EPI_WARPS) * 4, 1024);
+  return ASQ_OK;
+}
+
+int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
+                                 void* const* y_all, int y_dtype, int64_t M, int64_t N, int64_t K,
+                                 float dequant_scale, const float* col_scale, void* const* recv_all,
+                                 void* const* ctl_all, int rank, int world, void* stream) {
+  if (world < 2 || world > 8 || rank < 0 || rank >= world || y_all == nullptr || recv_all == nullptr || ctl_all == nullptr)
+    return fail(ASQ_ERR_INVALID, "allreduce: bad rank %d / world %d or null pointer tables", rank, world);
+  for (int r = 0; r < world; ++r)
+    if (y_all[r] == nullptr || recv_all[r] == nullptr || ctl_all[r] == nullptr || (reinterpret_cast<uintptr_t>(y_all[r]) & 15) ||
+        (reinterpret_cast<uintptr_t>(recv_all[r]) & 15))
+      return fail(ASQ_ERR_INVALID, "allreduce: rank %d buffers must be non-null and 16-byte aligned", r);
+  int rc = check_common(xq, w, y_all[rank], M, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (y_dtype != ASQ_BF16 && y_dtype != ASQ_F16) return fail(ASQ_ERR_INVALID, "allreduce: y dtype must be f16 or bf16");
+  if (N % 8 != 0) return fail(ASQ_ERR_INVALID, "allreduce: N=%lld must be a multiple of 8 (16-byte output rows)", (long long)N);
+  if (M == 0) return fail(ASQ_ERR_INVALID, "allreduce: M must be positive (every rank has to launch)");
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = y_all[rank]; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT;
+  p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
+  p.row_scale = const_cast<float*>(row_scale);
+  p.ar_world = world; p.ar_rank = rank;
+  void* peers[7];
+  int n = 0;
+  for (int r = 0; r < world; ++r) {
+    p.ar_ctl[r] = static_cast<uint32_t*>(ctl_all[r]);
+    p.ar_recv[r] = static_cast<uint32_t*>(recv_all[r]);
+    if (r != rank) peers[n++] = y_all[r];
+  }
+  return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream), peers);
+}
+
+// ---- device memory shared between the processes of one node (cudaMalloc + CUDA IPC), used for the buffers above
+int asq_dev_alloc(size_t bytes, void** ptr) {
+  if (ptr == nullptr || bytes == 0) return fail(ASQ_ERR_INVALID, "asq_dev_alloc: bad arguments");
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ASQ_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  e = cudaMemset(*ptr, 0, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ASQ_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+  return ASQ_OK;
+}
+int asq_dev_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ASQ_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e)); }
+  return ASQ_OK;
+}
+int asq_ipc_export(const void* dev_ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  if (dev_ptr == nullptr || handle64 == nullptr) return fail(ASQ_ERR_INVALID, "asq_ipc_export: null argument");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr));
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ASQ_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  memcpy(handle64, &h, 64);
+  return ASQ_OK;
+}
+int asq_ipc_open(const void* handle64, void** dev_ptr) {
+  if (dev_ptr == nullptr || handle64 == nullptr) return fail(ASQ_ERR_INVALID, "asq_ipc_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ASQ_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+  return ASQ_OK;
+}
+int asq_ipc_close(void* dev_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ASQ_ERR_CUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e)); }
+  return ASQ_OK;
 }
 
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c, int64_t M, int64_t N, int64_t K,

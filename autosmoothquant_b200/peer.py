@@ -1,0 +1,123 @@
+"""Peer-memory communicator for the row-parallel linear fused with its all-reduce.
+
+One process per GPU (``torch.distributed`` only carries the 64-byte CUDA IPC handles at set-up time): every
+rank allocates a receive buffer, control words and two output buffers with ``asq_dev_alloc`` (plain
+``cudaMalloc``, zero-filled), exports them, and maps the peers' buffers into its own address space.  After
+that ``PeerComm.linear_q8_allreduce`` is ONE kernel launch per rank and no NCCL call: partial int32
+accumulators travel by P2P stores over NVLink, finished tiles are TMA-stored into every rank's output
+(``include/asq.h``: ``asq_w8a8_linear_q8_allreduce``).
+
+Output buffers alternate between consecutive launches; a result stays valid until the launch after the next
+one on the same communicator (the protocol's end-of-launch handshake guarantees every rank has consumed the
+previous use by then, provided consumers are enqueued before the next launch — true for a sequential stream).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class _DevBuffer:
+    """cudaMalloc'ed memory exposed to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerComm:
+    def __init__(self, group=None, device: Optional[torch.device] = None, max_m: int = 2048, max_n: int = 8192,
+                 dtype: torch.dtype = torch.bfloat16):
+        if not dist.is_initialized():
+            raise RuntimeError("PeerComm needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if not 2 <= self.world <= 8:
+            raise ValueError("PeerComm supports 2..8 ranks of one node")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_m, self.max_n, self.dtype = int(max_m), int(max_n), dtype
+        lib = _lib.load()
+        recv_b, ctl_b = ctypes.c_size_t(), ctypes.c_size_t()
+        with torch.cuda.device(self.device):
+            _lib._check(lib.asq_ar_buffer_bytes(self.max_m, self.max_n, self.world, ctypes.byref(recv_b), ctypes.byref(ctl_b)))
+            y_bytes = self.max_m * self.max_n * 2
+            sizes = {"recv": recv_b.value, "ctl": ctl_b.value, "y0": y_bytes, "y1": y_bytes}
+            self._own = {}
+            handles = {}
+            for name, nbytes in sizes.items():
+                ptr = ctypes.c_void_p()
+                _lib._check(lib.asq_dev_alloc(nbytes, ctypes.byref(ptr)))
+                self._own[name] = (ptr.value, nbytes)
+                h = (ctypes.c_ubyte * 64)()
+                _lib._check(lib.asq_ipc_export(ptr, h))
+                handles[name] = bytes(h)
+            torch.cuda.synchronize(self.device)
+            gathered: List[dict] = [None] * self.world
+            dist.all_gather_object(gathered, handles, group=group)
+            self._opened = []
+            self.ptrs = {name: [0] * self.world for name in sizes}
+            for r in range(self.world):
+                for name in sizes:
+                    if r == self.rank:
+                        self.ptrs[name][r] = self._own[name][0]
+                    else:
+                        out = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(gathered[r][name])
+                        _lib._check(lib.asq_ipc_open(buf, ctypes.byref(out)))
+                        self._opened.append(out.value)
+                        self.ptrs[name][r] = out.value
+        self._tables = {name: (ctypes.c_void_p * self.world)(*self.ptrs[name]) for name in sizes}
+        self._y_views = [torch.as_tensor(_DevBuffer(*self._own[n]), device=self.device) for n in ("y0", "y1")]
+        self._launches = 0
+        dist.barrier(group=group)  # every rank's buffers exist, are zeroed and mapped before the first launch
+
+    def linear_q8_allreduce(self, xq: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                            dequant_scale: float, col_scale: Optional[torch.Tensor] = None,
+                            row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sum over ranks of (xq_r . weight_r^T), dequantised (+ bias) — xq [M, K/world] int8, weight [N, K/world]
+        int8, bias on EVERY rank.  Returns a [M, N] view of this rank's symmetric output buffer."""
+        if xq.dtype != torch.int8 or weight.dtype != torch.int8 or xq.dim() != 2 or xq.shape[1] != weight.shape[1]:
+            raise ValueError("linear_q8_allreduce expects int8 [M,K] activations and int8 [N,K] weights")
+        if not (xq.is_cuda and weight.is_cuda and xq.is_contiguous() and weight.is_contiguous()):
+            raise ValueError("linear_q8_allreduce expects contiguous CUDA tensors (no CPU fallback)")
+        M, K = xq.shape
+        N = weight.shape[0]
+        if M > self.max_m or N > self.max_n or M * N > self.max_m * self.max_n:
+            raise ValueError(f"[{M},{N}] exceeds the communicator's buffers [{self.max_m},{self.max_n}]")
+        # the receive-buffer layout depends on (M, N): it must not exceed what was allocated for (max_m, max_n)
+        lib = _lib.load()
+        recv_b, ctl_b = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib._check(lib.asq_ar_buffer_bytes(M, N, self.world, ctypes.byref(recv_b), ctypes.byref(ctl_b)))
+        if recv_b.value > self._own["recv"][1] or ctl_b.value > self._own["ctl"][1]:
+            raise ValueError("shape needs larger exchange buffers than this communicator allocated")
+        which = self._launches & 1
+        y_table = self._tables["y1" if which else "y0"]
+        with torch.cuda.device(self.device):
+            rc = lib.asq_w8a8_linear_q8_allreduce(
+                xq.data_ptr(), _lib._ptr(row_scale), weight.data_ptr(), _lib._ptr(bias), y_table, _lib._code(self.dtype),
+                M, N, K, float(dequant_scale), _lib._ptr(col_scale), self._tables["recv"], self._tables["ctl"],
+                self.rank, self.world, _lib._stream(self.device))
+        _lib._check(rc)
+        _lib._launches += 1
+        self._launches += 1
+        return self._y_views[which][: M * N * 2].view(self.dtype).view(M, N)
+
+    def close(self) -> None:
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for ptr in self._opened:
+                lib.asq_ipc_close(ctypes.c_void_p(ptr))
+            self._opened = []
+            dist.barrier(group=self.group)
+            for ptr, _ in self._own.values():
+                lib.asq_dev_free(ctypes.c_void_p(ptr))
+            self._own = {}

@@ -119,10 +119,13 @@ class RowParallelLinear(nn.Module):
     """
 
     def __init__(self, shard: nn.Module, group=None, reduce: str = "native", local_scales: bool = False,
-                 backend=CudaBackend, has_bias: Optional[bool] = None):
+                 backend=CudaBackend, has_bias: Optional[bool] = None, comm=None):
         super().__init__()
-        if reduce not in ("native", "fp32", "int32"):
-            raise ValueError("reduce must be 'native' (activation dtype), 'fp32' or 'int32'")
+        if reduce not in ("native", "fp32", "int32", "fused"):
+            raise ValueError("reduce must be 'native' (activation dtype), 'fp32', 'int32' or 'fused'")
+        if reduce == "fused" and comm is None:
+            raise ValueError("reduce='fused' needs a peer.PeerComm (GEMM + all-reduce in one kernel over peer memory)")
+        self.comm = comm
         self.shard, self.group, self.reduce, self.local_scales, self.backend = shard, group, reduce, local_scales, backend
         self.has_bias = shard.use_bias if has_bias is None else has_bias
         self.in_features, self.out_features = shard.in_features, shard.out_features
@@ -155,6 +158,16 @@ class RowParallelLinear(nn.Module):
             mode, qs = _lib.ACT_SCALE, float(m.quant_scale.item())
         else:
             mode, qs = _lib.ACT_ROUND, 1.0
+
+        if self.reduce == "fused":
+            # ONE launch per rank, no NCCL: int32 partials over NVLink peer stores, owner-side exact sum and the
+            # unsharded module's fp32 epilogue, finished tiles stored into every rank's output (peer.PeerComm)
+            if mode == _lib.ACT_PER_TOKEN:
+                raise NotImplementedError("reduce='fused' needs global row scales (local_scales=False)")
+            q, _ = _lib.quantize_act(x2, mode, qs, row_scale=row_scale)
+            y = self.comm.linear_q8_allreduce(q, m.weight, self._bias_everywhere(x2.device),
+                                              float(m.dequant_scale.item()), row_scale=row_scale)
+            return y.view(*x.shape[:-1], m.out_features)
 
         if self.reduce == "int32":
             # exactness mode: sum the integer accumulators, then the unsharded module's fp32 epilogue

@@ -179,6 +179,31 @@ int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const in
                               float gate_dequant_scale, float up_dequant_scale, const float* col_scale_il,
                               float out_quant_scale, int div_mode, void* stream);
 
+/* ---- Row-parallel linear fused with its all-reduce over NVLink peer memory (SURVEY 8(e) "fusion target").
+ * One launch per rank replaces asq_w8a8_linear_q8 + ncclAllReduce(sum): every rank computes all output tiles
+ * over its K shard; tile t is owned by rank t % world; non-owners store their raw int32 accumulators into the
+ * owner's receive buffer (P2P stores) and raise a flag; the owner adds them (exact integer sum, so the result
+ * is bit-identical to the unsharded module), applies the fp32 dequant epilogue (+ bias) and TMA-stores the
+ * finished 16-bit tile into the y buffer of every rank.  Ranks walk the tiles they do not own first, so the
+ * exchange overlaps the remaining math tile by tile.  No NCCL call is involved.
+ *   y_all / recv_all / ctl_all   [world] device pointers valid in THIS process: entry r is rank r's output,
+ *       receive and control buffer (own buffers from asq_dev_alloc, the peers' via asq_ipc_open).  Sizes from
+ *       asq_ar_buffer_bytes for the largest (M, N) used; zero-filled at allocation, never reset by the host.
+ *   bias (fp32 [N]) must be given on EVERY rank (the tile owner applies it); row_scale = global per-token scales.
+ * Every rank of the group must issue the same sequence of these calls (same shapes); a launch returns only
+ * after every peer has finished writing this rank's y.  y may be reused by the launch after the next one. */
+int asq_ar_buffer_bytes(int64_t M, int64_t N, int world, size_t* recv_bytes, size_t* ctl_bytes);
+int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
+                                 void* const* y_all, int y_dtype, int64_t M, int64_t N, int64_t K,
+                                 float dequant_scale, const float* col_scale, void* const* recv_all,
+                                 void* const* ctl_all, int rank, int world, void* stream);
+/* Zero-filled cudaMalloc memory and CUDA IPC handles (64 bytes) to map it into the other ranks' processes. */
+int asq_dev_alloc(size_t bytes, void** ptr);
+int asq_dev_free(void* ptr);
+int asq_ipc_export(const void* dev_ptr, void* handle64);
+int asq_ipc_open(const void* handle64, void** dev_ptr);
+int asq_ipc_close(void* dev_ptr);
+
 /* c[M,N] (int32) = a[M,K] (int8) . w[N,K]^T (int8), exact.  Drop-in for
  * I8CUGEMM::linear_a8_w8_o32_ and the exactness tap of the fused kernels. */
 int asq_i8gemm_o32(const int8_t* a, const int8_t* w, int32_t* c,

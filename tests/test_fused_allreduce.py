@@ -1,0 +1,109 @@
+"""Row-parallel GEMM fused with its all-reduce over NVLink peer memory (needs >= 2 CUDA devices).
+
+world_size 2, one process per GPU.  The fused launch exchanges int32 accumulators, so its output must equal
+the UNSHARDED single-GPU module bit for bit (same bar as reduce="int32" over NCCL) — per-tensor and per-token,
+with bias, over M / N tile tails, across repeated launches (epoch handshake, alternating output buffers) and
+shapes that use CTA pairs as well as single-CTA tiles.  The workers run under a watchdog: a protocol deadlock
+fails the test instead of hanging the box.
+"""
+import os
+import socket
+import time
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(300, 768, 1024), (2048, 4096, 4096), (64, 512, 2048), (1000, 1000 // 8 * 8, 512), (2048, 4096, 11008 // 32 * 32)]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    results = {}
+    try:
+        from autosmoothquant_b200 import _lib, peer, tp
+        from autosmoothquant_b200.layers.nn.linear import W8A8BFP32OFP32LinearWithQuantScale
+
+        comm = peer.PeerComm(device=dev, max_m=2048, max_n=4096)
+        # 1. raw entry point against the exact integer GEMM of the whole K, several shapes, two launches each
+        g = torch.Generator().manual_seed(5)
+        for (M, N, K) in SHAPES:
+            a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+            w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(dev)
+            b = torch.randn(N, generator=g).to(dev)
+            rs = (torch.rand(M, generator=g) + 0.5).to(dev)
+            want = _lib.w8a8_linear_q8(a, w, b, 3e-5, row_scale=rs)
+            lo, hi = rank * K // world, (rank + 1) * K // world
+            for rep in range(2):
+                got = comm.linear_q8_allreduce(a[:, lo:hi].contiguous(), w[:, lo:hi].contiguous(), b, 3e-5, row_scale=rs)
+                torch.cuda.synchronize()
+                results[f"raw {M}x{N}x{K} #{rep}"] = bool(torch.equal(got, want))
+        # 2. module level: RowParallelLinear(reduce="fused") == the unsharded module, bit for bit
+        torch.manual_seed(0)
+        K, N = 1024, 768
+        lin = torch.nn.Linear(K, N, bias=True)
+        x = torch.randn(300, K).to(torch.bfloat16).to(dev)
+        for act in ("per-tensor", "per-token"):
+            full = W8A8BFP32OFP32LinearWithQuantScale.from_float(lin, 0.05, act_quant=act).to(dev)
+            want = full(x)
+            row = tp.RowParallelLinear(tp.shard_row(full, rank, world).to(dev), reduce="fused", has_bias=True, comm=comm)
+            lo, hi = rank * K // world, (rank + 1) * K // world
+            got = row(x[:, lo:hi].contiguous())
+            torch.cuda.synchronize()
+            results[f"module fused {act}"] = bool(torch.equal(got, want))
+        # 3. back-to-back launches without host synchronisation (the handshake alone must order them)
+        M, N, K = 512, 1024, 2048
+        a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+        w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(dev)
+        want = _lib.w8a8_linear_q8(a, w, None, 1e-4)
+        lo, hi = rank * K // world, (rank + 1) * K // world
+        al, wl = a[:, lo:hi].contiguous(), w[:, lo:hi].contiguous()
+        ok = True
+        for _ in range(20):
+            got = comm.linear_q8_allreduce(al, wl, None, 1e-4)
+            ok = ok and bool(torch.equal(got.clone(), want))
+        torch.cuda.synchronize()
+        results["20 launches back to back"] = ok
+        comm.close()
+    except Exception as e:  # noqa: BLE001
+        results["exception"] = repr(e)
+    finally:
+        ret[rank] = results
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def test_fused_gemm_allreduce_world2_bit_exact():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    ctx = mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=False)
+    deadline = time.time() + 240
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for proc in ctx.processes:
+                if proc.is_alive():
+                    proc.kill()
+            pytest.fail(f"fused all-reduce workers did not finish within 240 s (deadlock?); partial results: {dict(ret)}")
+    assert len(ret) == world
+    for rank in range(world):
+        assert "exception" not in ret[rank], f"rank {rank}: {ret[rank]['exception']}"
+        assert len(ret[rank]) >= 2 * len(SHAPES) + 3
+        for name, ok in ret[rank].items():
+            assert ok, f"rank {rank}: {name} differs from the unsharded result"
