@@ -283,6 +283,12 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
         gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
                                  col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
         a8, _ = _lib.silu_mul_quant(gu, float(down.quant_scale.item()))
+    comm = getattr(layer, "peer_comm", None)
+    if tp_world > 1 and comm is not None:
+        # row-parallel GEMM + all-reduce in ONE launch over NVLink peer memory (exact int32 partial sums)
+        d = comm.linear_q8_allreduce(a8, down.weight, layer.down_proj._bias_everywhere(x2.device),
+                                     float(down.dequant_scale.item()))
+        return x2, d
     d = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
                             out_dtype=x2.dtype)
     if tp_world > 1:  # row-parallel partial sums -> one all-reduce over NVLink

@@ -217,17 +217,26 @@ def _shard_fused_columns(fused, rank: int, world: int, device):
 
 
 def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: Optional[Dict[str, str]] = None,
-                     group=None, dtype=torch.bfloat16, seed: int = 0, glue: bool = True):
+                     group=None, dtype=torch.bfloat16, seed: int = 0, glue: bool = True, fused_allreduce: bool = False,
+                     max_tokens: int = 2048):
     """The benchmark stack of ``harness.QuantDecoder`` tensor-parallel over `world` ranks: fused q|k|v and
     gate|up column-sharded by head / by intermediate channel, o_proj and down_proj row-sharded with ONE
     all-reduce each (NCCL over NVLink), attention over the local heads, residual stream and norms replicated.
-    Every rank builds the same seeded full-size layer and keeps its shard (one layer at a time)."""
+    Every rank builds the same seeded full-size layer and keeps its shard (one layer at a time).
+    fused_allreduce=True replaces (GEMM launch + NCCL all-reduce) of the two row-parallel projections by the
+    single-launch peer-memory kernel of ``peer.PeerComm`` (``max_tokens`` = largest batch*seq it will see)."""
     from . import harness
 
     model = harness.QuantDecoder(cfg, quant_config, device=device, dtype=dtype, seed=seed, layers=layers,
                                  fuse_projections=True, glue=glue, swiglu_epilogue=False)
     if model.qcfg["type"] != "int8":
         raise NotImplementedError("tensor-parallel fp8 stack")
+    comm = None
+    if fused_allreduce and world > 1:
+        from .peer import PeerComm
+
+        comm = PeerComm(group=group, device=device, max_m=max_tokens, max_n=cfg.hidden, dtype=dtype)
+    model.peer_comm = comm
     for layer in model.layers:
         layer.qkv_proj = _shard_fused_columns(layer.qkv_proj, rank, world, device)
         layer.qkv_sizes = list(layer.qkv_proj.qkv_size)
@@ -237,8 +246,9 @@ def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: O
         for name in ("o_proj", "down_proj"):
             full = getattr(layer, name)
             setattr(layer, name, RowParallelLinear(shard_row(full, rank, world).to(device), group=group,
-                                                   has_bias=full.use_bias))
-        layer.tp_world, layer.tp_group = world, group
+                                                   has_bias=full.use_bias, reduce="fused" if comm is not None else "native",
+                                                   comm=comm))
+        layer.tp_world, layer.tp_group, layer.peer_comm = world, group, comm
         torch.cuda.empty_cache()
     model.tp_world = world
     return model

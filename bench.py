@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
     ap.add_argument("--parallel", default="dp", choices=["dp", "tp"])
+    ap.add_argument("--tp-reduce", default="auto", choices=["auto", "fused", "nccl"],
+                    help="--parallel tp: row-parallel GEMM fused with its all-reduce over peer memory (one launch), "
+                         "or GEMM launch + NCCL all-reduce; auto = fused at 2 GPUs (measured faster), NCCL (NVLS) beyond")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-glue", action="store_true",
@@ -195,10 +198,13 @@ def run_ours(args, cfg, layers):
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    if args.tp_reduce == "auto":
+        args.tp_reduce = "fused" if world == 2 else "nccl"
     if args.parallel == "tp" and world > 1:
         from autosmoothquant_b200.tp import build_tp_decoder
 
-        model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank, glue=not args.no_glue)
+        model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank, glue=not args.no_glue,
+                                 fused_allreduce=args.tp_reduce == "fused", max_tokens=args.batch * world * args.seq)
         batch = args.batch * world  # weak scaling: the global batch grows with the GPU count
     else:
         model = QuantDecoder(cfg, device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
@@ -315,6 +321,20 @@ def run_ours(args, cfg, layers):
 
         for name, fn in originals.items():
             setattr(_lib, name, timed(fn))
+        from autosmoothquant_b200 import peer as _peer
+
+        peer_original = _peer.PeerComm.linear_q8_allreduce
+
+        def peer_timed(self, xq, weight, *a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = peer_original(self, xq, weight, *a, **kw)
+            e.record()
+            events.append((s, e, 2.0 * xq.shape[0] * xq.shape[1] * weight.shape[0],
+                           ("linear_q8_allreduce(fused)", xq.shape[0], weight.shape[0], xq.shape[1])))
+            return out
+
+        _peer.PeerComm.linear_q8_allreduce = peer_timed
         try:
             model(ids_dev)  # one warm instrumented pass
             torch.cuda.synchronize()
@@ -325,6 +345,7 @@ def run_ours(args, cfg, layers):
             model(ids_dev)
             torch.cuda.synchronize()
         finally:
+            _peer.PeerComm.linear_q8_allreduce = peer_original
             for name, fn in originals.items():
                 setattr(_lib, name, fn)
         by_shape = {}
@@ -372,6 +393,7 @@ def run_ours(args, cfg, layers):
                             f"batch {args.batch} x seq {S} per GPU, bf16 activations",
                 "layers": layers, "global_batch": B * replicas, "seq_len": S,
                 "parallelism": f"{args.parallel}{world}", "cuda_graph": graph is not None,
+                **({"tp_reduce": args.tp_reduce} if args.parallel == "tp" and world > 1 else {}),
                 "projections": "q|k|v and gate|up fused per layer (4 GEMM launches/layer)"
                                if not args.no_fuse else "one launch per projection (7 launches/layer)",
                 "glue": ("add+RMSNorm->int8 and in-place RoPE kernels feed the GEMMs (asq_glue.cu); SiLU(gate)*up and "

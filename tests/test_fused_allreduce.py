@@ -1,6 +1,6 @@
 """Row-parallel GEMM fused with its all-reduce over NVLink peer memory (needs >= 2 CUDA devices).
 
-world_size 2, one process per GPU.  The fused launch exchanges int32 accumulators, so its output must equal
+world_size 2 (and 4 / 8 when the box has the GPUs), one process per GPU.  The fused launch exchanges int32 accumulators, so its output must equal
 the UNSHARDED single-GPU module bit for bit (same bar as reduce="int32" over NCCL) — per-tensor and per-token,
 with bias, over M / N tile tails, across repeated launches (epoch handshake, alternating output buffers) and
 shapes that use CTA pairs as well as single-CTA tiles.  The workers run under a watchdog: a protocol deadlock
@@ -45,7 +45,8 @@ def _worker(rank, world, port, ret):
             b = torch.randn(N, generator=g).to(dev)
             rs = (torch.rand(M, generator=g) + 0.5).to(dev)
             want = _lib.w8a8_linear_q8(a, w, b, 3e-5, row_scale=rs)
-            lo, hi = rank * K // world, (rank + 1) * K // world
+            step = K // world // 16 * 16  # 16-byte aligned K shards; the last rank takes the remainder
+            lo, hi = rank * step, (K if rank == world - 1 else (rank + 1) * step)
             for rep in range(2):
                 got = comm.linear_q8_allreduce(a[:, lo:hi].contiguous(), w[:, lo:hi].contiguous(), b, 3e-5, row_scale=rs)
                 torch.cuda.synchronize()
@@ -87,10 +88,10 @@ def _worker(rank, world, port, ret):
             pass
 
 
-def test_fused_gemm_allreduce_world2_bit_exact():
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 CUDA devices")
-    world = 2
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_gemm_allreduce_bit_exact(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} CUDA devices")
     mgr = mp.Manager()
     ret = mgr.dict()
     ctx = mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=False)

@@ -52,6 +52,13 @@ def _worker(rank, world, port, ret):
             model = tp.build_tp_decoder(harness.TINY, layers=None, device=dev, world=world, rank=rank, seed=3, glue=glue)
             out = model(ids, last_token_only=False)
             results[f"decoder glue={glue}"] = bool(float((out - ref).abs().max()) <= 0.08 * float(ref.abs().max()))
+        model = tp.build_tp_decoder(harness.TINY, layers=None, device=dev, world=world, rank=rank, seed=3, glue=True,
+                                    fused_allreduce=True, max_tokens=128)
+        out = model(ids, last_token_only=False)
+        results["decoder fused all-reduce"] = bool(float((out - ref).abs().max()) <= 0.08 * float(ref.abs().max()))
+        out2 = model(ids, last_token_only=False)
+        results["decoder fused all-reduce repeatable"] = bool(torch.equal(out, out2))
+        model.peer_comm.close()
         ret[rank] = results
     finally:
         dist.destroy_process_group()
