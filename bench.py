@@ -95,10 +95,61 @@ def cpu_layer_sample(cfg, seq, threads):
     return t_total
 
 
+def reference_native_gpu_sample(cfg, seq, layers):
+    """The reference's OWN hot path on this GPU, as a second baseline next to the CPU one: the eager launches of
+    W8A8BFP32OFP32Linear(.WithQuantScale).forward (linear.py:83-106, 278-302) around the reference's unmodified
+    native GEMM (oracle/_ref = csrc/int8gemm built by oracle/build_ref.py), seven separate projections per
+    decoder layer as the reference's model classes issue them.  Linears only, bf16 activations."""
+    import torch
+
+    from oracle import build_ref
+
+    if not (torch.cuda.is_available() and build_ref.available()):
+        return None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gemm = build_ref.load().I8CUGEMM()
+    h, inter, kv = cfg.hidden, cfg.intermediate, cfg.kv_heads * cfg.head_dim
+    shapes = [(h, h, None), (kv, h, None), (kv, h, None), (h, h, 0.05), (inter, h, None), (inter, h, None), (h, inter, 0.06)]
+    g = torch.Generator(device=dev).manual_seed(0)
+    ws = [torch.randint(-127, 128, (n, k), dtype=torch.int8, device=dev, generator=g) for n, k, _ in shapes]
+    xs = [(torch.randn(seq, k, device=dev, generator=g) * (30.0 if qs is None else 1.0)).to(torch.bfloat16) for _, k, qs in shapes]
+
+    def layer():
+        for (n, k, qs), wt, x in zip(shapes, ws, xs):
+            q = (x.round() if qs is None else (x / qs).round()).clamp(-128, 127).to(torch.int8)
+            out = torch.empty(seq, n, dtype=torch.int32, device=dev)
+            gemm.linear_a8_w8_o32_(q, wt, out)
+            (0.003 * out).to(x.dtype)
+
+    for _ in range(3):
+        layer()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        layer()
+    e1.record()
+    torch.cuda.synchronize()
+    t_layer = e0.elapsed_time(e1) / iters * 1e-3
+    ops = 2.0 * seq * sum(n * k for n, k, _ in shapes)
+    return {"linears_ms_per_step": t_layer * layers * 1e3, "tops": ops / t_layer / 1e12,
+            "what": "reference eager prologue/epilogue + its own cuBLASLt INT8 GEMM (oracle/_ref) on this GPU, "
+                    f"7 projections/layer x {layers} layers, quantized linears only"}
+
+
 def cpu_baseline(cfg, seq, layers):
     threads = os.cpu_count() or 1
     t_layer = cpu_layer_sample(cfg, seq, threads)
+    extra = {}
+    try:
+        ref_gpu = reference_native_gpu_sample(cfg, seq, layers)
+        if ref_gpu is not None:
+            extra["reference_native_gpu"] = ref_gpu
+    except Exception as e:  # noqa: BLE001
+        extra["reference_native_gpu"] = {"unavailable": repr(e)[:200]}
     return {
+        **extra,
         "value": seq / (t_layer * layers),
         "unit": UNIT,
         "cores": threads,
