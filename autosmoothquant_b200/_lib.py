@@ -16,7 +16,7 @@ from typing import Optional, Tuple
 import torch
 
 _PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libasq_b200.so"
+LIB_PATH = _PKG_DIR / os.environ.get("ASQ_LIB_NAME", "libasq_b200.so")  # ASQ_LIB_NAME: experiment builds only
 
 # enums of include/asq.h
 ASQ_F32, ASQ_F16, ASQ_BF16, ASQ_I32, ASQ_I8 = 0, 1, 2, 3, 4
@@ -46,6 +46,7 @@ EXPORTED_SYMBOLS = (
     "asq_w8a8_linear_q8",
     "asq_w8a8_gateup_swiglu_q8",
     "asq_w8a8_linear_q8_rope",
+    "asq_w8a8_grouped_linear",
     "asq_ar_buffer_bytes",
     "asq_w8a8_linear_q8_allreduce",
     "asq_dev_alloc",
@@ -128,6 +129,9 @@ def load():
         lib.asq_w8a8_linear_q8_rope.restype = c_i
         lib.asq_w8a8_linear_q8_rope.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
                                                 c_vp, c_vp, c_i64, c_i64, c_i64, c_i, c_vp]
+        lib.asq_w8a8_grouped_linear.restype = c_i
+        lib.asq_w8a8_grouped_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_vp, c_vp, c_vp, c_vp,
+                                                c_i, c_vp, c_i, c_i, c_vp, c_sz, c_vp]
         c_pp = ctypes.POINTER(ctypes.c_void_p)
         lib.asq_ar_buffer_bytes.restype = c_i
         lib.asq_ar_buffer_bytes.argtypes = [c_i64, c_i64, c_i, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]
@@ -512,6 +516,48 @@ def w8a8_gateup_swiglu(
     _check(rc)
     _launches += 1
     return out
+
+
+def w8a8_grouped_linear(
+    x: torch.Tensor,
+    weight_stacked: torch.Tensor,
+    group_of_blk: torch.Tensor,
+    group_dequant_scale: torch.Tensor,
+    act_mode: int,
+    group_quant_scale: Optional[torch.Tensor] = None,
+    group_dequant_scale_up: Optional[torch.Tensor] = None,
+    swiglu: bool = False,
+    div_mode: Optional[int] = None,
+) -> torch.Tensor:
+    """All experts of an MoE block in one launch (include/asq.h: asq_w8a8_grouped_linear).  x [M_pad, K] holds the
+    routed rows sorted by expert, every expert's segment padded to a multiple of 256 rows; group_of_blk (int32
+    [M_pad / 128]) names the expert of each 128-row block (-1: unused); weight_stacked [G * N, K]."""
+    global _launches
+    dev = _require_cuda(x, weight_stacked, group_of_blk, group_dequant_scale, group_quant_scale, group_dequant_scale_up)
+    G = group_dequant_scale.numel()
+    if x.dim() != 2 or weight_stacked.dtype != torch.int8 or weight_stacked.shape[1] != x.shape[1] or weight_stacked.shape[0] % G:
+        raise ValueError("w8a8_grouped_linear expects x [M_pad,K] and stacked int8 weights [G*N,K]")
+    if group_of_blk.dtype != torch.int32 or group_of_blk.numel() * 128 < x.shape[0]:
+        raise ValueError("group_of_blk must be int32 with one entry per 128 rows of x")
+    if not (x.is_contiguous() and weight_stacked.is_contiguous() and group_of_blk.is_contiguous()):
+        raise ValueError("w8a8_grouped_linear expects contiguous tensors")
+    M, K = x.shape
+    N = weight_stacked.shape[0] // G
+    out_dtype = x.dtype
+    y = torch.empty((M, N // 2 if swiglu else N), dtype=out_dtype, device=dev)
+    if M == 0:
+        return y
+    lib = load()
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(M, K))
+        rc = lib.asq_w8a8_grouped_linear(
+            x.data_ptr(), _code(x.dtype), weight_stacked.data_ptr(), y.data_ptr(), _code(out_dtype), M, N, K, G,
+            group_of_blk.data_ptr(), group_dequant_scale.data_ptr(), _ptr(group_dequant_scale_up), _ptr(group_quant_scale),
+            act_mode, None, 1 if swiglu else 0, _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream)
+    _check(rc)
+    _launches += 1
+    return y
 
 
 def add_rmsnorm_quant(

@@ -16,7 +16,8 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 SOURCES = [PKG_DIR / "csrc" / "asq_kernels.cu", PKG_DIR / "csrc" / "asq_glue.cu"]
 HEADERS = [PKG_DIR / "csrc" / "asq_ptx.cuh", REPO_ROOT / "include" / "asq.h"]
-LIB_PATH = PKG_DIR / "libasq_b200.so"
+# experiments: ASQ_LIB_NAME=libasq_b200_x.so ASQ_NVCC_DEFS="-DASQ_EPI_NBUF=1" builds (and _lib loads) a variant library
+LIB_PATH = PKG_DIR / os.environ.get("ASQ_LIB_NAME", "libasq_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,7 +41,7 @@ def needs_build() -> bool:
 
 
 N_KERNEL_TUS = 6  # asq_kernels.cu is compiled once per kernel instantiation (-DASQ_TU=1..6) + once for the host side (0)
-OBJ_DIR = Path(os.environ.get("ASQ_OBJ_DIR", "/tmp/asq_b200_obj"))  # objects stay out of the tree
+OBJ_DIR = Path(os.environ.get("ASQ_OBJ_DIR", "/tmp/asq_b200_obj" + ("_" + os.environ["ASQ_LIB_NAME"] if "ASQ_LIB_NAME" in os.environ else "")))  # objects stay out of the tree
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -50,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     nvcc = find_nvcc()
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
-    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-c"]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-c"] + os.environ.get("ASQ_NVCC_DEFS", "").split()
     if verbose:
         compile_flags += ["-Xptxas", "-v"]
     jobs = []

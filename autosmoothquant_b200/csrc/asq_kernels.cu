@@ -86,6 +86,7 @@ struct LinearParams {
   int M, N, K;
   int x_dtype, y_dtype, bias_dtype, act_mode, div_mode, epi_kind, flags;
   int num_m_blocks, num_n_blocks, num_k_blocks, group, raster_m;  // num_n_blocks = TILE_N-wide tiles per row
+  int tile_m_blocks;                                              // 128-row blocks per M tile (1, or 2 for CTA pairs)
   int n_units, tile_units, rounds, tail_tiles;                    // schedule (see TileWalk)
   // stream-K tail: the k-iterations of the left-over tiles are dealt evenly to all workers; partial
   // accumulators travel through `sk_partial` (one 128-row x 256-column fp32/int32 slot per CTA), handshake
@@ -93,6 +94,16 @@ struct LinearParams {
   int sk_enabled, sk_total, sk_workers;  // sk_workers <= launched workers: every participant gets >= 1 iteration
   uint32_t* sk_partial;
   uint32_t* sk_flags;
+  // Grouped GEMM (MoE experts): the rows of x are sorted by group and every group's segment is padded to a
+  // multiple of 256 rows; group_of_blk[row / 128] names the group (expert) of a 128-row block, -1 = padding block
+  // (its tiles are skipped).  Group g multiplies by weight rows [g * N, (g + 1) * N) of the stacked [G * N, K]
+  // matrix and dequantises with group_scale[g] (SwiGLU: up columns with group_scale_up[g]); the per-tensor
+  // activation scale of phase 1 is group_quant_scale[g] when given.
+  const int* group_of_blk;
+  const float* group_scale;
+  const float* group_scale_up;
+  const float* group_quant_scale;
+  int num_groups;
   // Row-parallel GEMM fused with its all-reduce over peer memory (NVLink P2P): every rank computes the partial
   // of every tile over its K shard; tile t is OWNED by rank t % world.  Non-owners push their raw int32 / fp32
   // accumulators into the owner's receive buffer and raise a flag; the owner adds them to its own accumulator
@@ -265,8 +276,8 @@ __device__ __forceinline__ void quantize_vec(const uint4& v, uint8_t* dst, float
   for (int i = 0; i < VEC; i += 2) {
     float a = f[i], b = f[i + 1];
     if (QM == QM_ROW_DIV) { a = __fdiv_rn(a, scale); b = __fdiv_rn(b, scale); }
-    else if (QM == QM_SCALE_RECIP) { a = __fmul_rn(a, p.inv_quant_scale); b = __fmul_rn(b, p.inv_quant_scale); round_pair_t<T>(a, b); }
-    else if (QM == QM_SCALE_DIV) { a = __fdiv_rn(a, p.quant_scale); b = __fdiv_rn(b, p.quant_scale); round_pair_t<T>(a, b); }
+    else if (QM == QM_SCALE_RECIP) { a = __fmul_rn(a, scale); b = __fmul_rn(b, scale); round_pair_t<T>(a, b); }  // scale = 1/qs
+    else if (QM == QM_SCALE_DIV) { a = __fdiv_rn(a, scale); b = __fdiv_rn(b, scale); round_pair_t<T>(a, b); }    // scale = qs
     else if (QM == QM_TENSOR_DYN) { a = __fdiv_rn(a, scale); b = __fdiv_rn(b, scale); round_pair_t<T>(a, b); }
     f[i] = a;
     f[i + 1] = b;
@@ -351,7 +362,7 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
       if (c < K) quantize_vec<T, FP8, QM>(buf[j], qrow + c, scale, p);
     }
   }
-  return (QM == QM_ROW_DIV || QM == QM_TENSOR_DYN) ? scale : 0.f;
+  return (QM == QM_ROW_DIV || QM == QM_TENSOR_DYN) ? scale : 0.f;  // QM_SCALE_*: `scale` carried 1/qs or qs, not a row scale
 }
 
 template <typename T, bool FP8>
@@ -366,9 +377,16 @@ __device__ __forceinline__ float quantize_row_typed(const LinearParams& p, int r
       return quantize_row<T, FP8, QM_ROW_DIV>(xrow, qrow, p.K, lane, p, __ldg(p.row_scale_in + row), false);
     case ASQ_ACT_PER_TENSOR_DYNAMIC:
       return quantize_row<T, FP8, QM_TENSOR_DYN>(xrow, qrow, p.K, lane, p, tensor_scale, false);
-    case ASQ_ACT_SCALE:
-      return (p.div_mode == ASQ_DIV_RECIPROCAL) ? quantize_row<T, FP8, QM_SCALE_RECIP>(xrow, qrow, p.K, lane, p, 0.f, false)
-                                                : quantize_row<T, FP8, QM_SCALE_DIV>(xrow, qrow, p.K, lane, p, 0.f, false);
+    case ASQ_ACT_SCALE: {
+      float qs = p.quant_scale, inv = p.inv_quant_scale;
+      if (p.group_quant_scale != nullptr) {  // grouped launch: every expert has its own input scale
+        const int grp = __ldg(p.group_of_blk + row / BLOCK_M);
+        qs = grp >= 0 ? __ldg(p.group_quant_scale + grp) : 1.f;
+        inv = __frcp_rn(qs);  // == the host's 1.0f / qs
+      }
+      return (p.div_mode == ASQ_DIV_RECIPROCAL) ? quantize_row<T, FP8, QM_SCALE_RECIP>(xrow, qrow, p.K, lane, p, inv, false)
+                                                : quantize_row<T, FP8, QM_SCALE_DIV>(xrow, qrow, p.K, lane, p, qs, false);
+    }
     default:
       return quantize_row<T, FP8, QM_ROUND>(xrow, qrow, p.K, lane, p, 0.f, false);
   }
@@ -716,7 +734,10 @@ __device__ __forceinline__ void tile_coords(int t, const LinearParams& p, int& m
 constexpr int TILE_N = 256;
 constexpr int UNIT_N = 64;
 constexpr uint32_t EPI_BUF_BYTES = 32 * 128;  // one warp's staging tile: 32 rows x 128 bytes
-constexpr uint32_t EPI_NBUF = 2;              // double-buffered per warp
+#ifndef ASQ_EPI_NBUF
+#define ASQ_EPI_NBUF 2
+#endif
+constexpr uint32_t EPI_NBUF = ASQ_EPI_NBUF;   // staging buffers per warp
 constexpr uint32_t EPI_BYTES = NUM_EPI_WARPS * EPI_BUF_BYTES * EPI_NBUF;
 constexpr uint32_t SMEM_LIMIT = 232448;       // 227 KB per CTA on sm_100
 
@@ -748,6 +769,7 @@ struct Seg {
   int role;                // SEG_COMPLETE: whole K, normal epilogue; SEG_CONTRIB: writes a partial; SEG_OWNER: adds partials
   int tile_g0;             // owner: first stream-K iteration index of its tile
   int ar_tile;             // all-reduce mode: linear tile id (owner = ar_tile % world, slot = ar_tile / world)
+  int group;               // grouped GEMM: the group (expert) of this tile's rows, 0 otherwise
 };
 enum : int { SEG_COMPLETE = 0, SEG_CONTRIB = 1, SEG_OWNER = 2, SEG_AR_CONTRIB = 3, SEG_AR_OWNER = 4 };
 
@@ -782,6 +804,7 @@ struct TileWalk {
       sg.role = (owner == p.ar_rank) ? SEG_AR_OWNER : SEG_AR_CONTRIB;
     }
     tile_coords(t, p, sg.m_blk, n_blk);
+    sg.group = (p.group_of_blk != nullptr) ? __ldg(p.group_of_blk + sg.m_blk * p.tile_m_blocks) : 0;
     const int U = p.tile_units;  // tile width in 64-column units: 4, or fewer for decode-sized problems
     sg.col0 = n_blk * U * UNIT_N;
     sg.width = min(U, p.n_units - n_blk * U) * UNIT_N;
@@ -791,16 +814,19 @@ struct TileWalk {
     sg.kb1 = p.num_k_blocks;
     sg.role = SEG_COMPLETE;
     sg.tile_g0 = 0;
-    if (round < p.rounds) {
+    while (round < p.rounds) {
       set_tile(sg, round * W + worker);
       ++round;
-      return true;
+      if (sg.group >= 0) return true;  // group -1: padding rows of a grouped launch, nothing to compute
     }
     if (g >= g_end) return false;
     if (!p.sk_enabled) {
-      set_tile(sg, p.rounds * W + g);
-      ++g;
-      return true;
+      while (g < g_end) {
+        set_tile(sg, p.rounds * W + g);
+        ++g;
+        if (sg.group >= 0) return true;
+      }
+      return false;
     }
     // stream-K: this worker's share [g, g_end) of the tail's k-iterations, cut at tile boundaries
     const int nkb = p.num_k_blocks;
@@ -930,7 +956,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (width <= 0) width = UNIT_N;
         const int row0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's A rows
         const int b_rows = width / CG;                                                  // this CTA's W rows
-        const int w_row = col0 + static_cast<int>(cta_rank) * b_rows;
+        const int w_row = sg.group * p.N + col0 + static_cast<int>(cta_rank) * b_rows;  // group > 0: stacked expert weights
         const uint32_t stage_tx = CG * (Cfg::A_BYTES + static_cast<uint32_t>(b_rows) * BLOCK_K);
         bool panel_ready = !fused || row0 >= p.M;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
@@ -1032,6 +1058,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool tensor_dyn = (p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC);
       const float ts = tensor_dyn ? tensor_scale_phase(p, ew * gridDim.x + blockIdx.x, warps_total, warps_total, lane) : 0.f;
       for (int row = ew * gridDim.x + blockIdx.x; row < p.M; row += warps_total) {
+        if (p.group_of_blk != nullptr && __ldg(p.group_of_blk + row / BLOCK_M) < 0) continue;  // padding block of a grouped launch
         const float s = quantize_row_any<FP8>(p, row, lane, ts);
         if (lane == 0 && (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN || tensor_dyn)) {
           p.row_scale[row] = s;
@@ -1074,6 +1101,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
       const int ngroups = width / UNIT_N;
       float rs = 0.f;
+      const float tile_scale = (p.group_scale != nullptr) ? __ldg(p.group_scale + sg.group) : p.dequant_scale;
+      const float tile_scale_up = (p.group_scale_up != nullptr) ? __ldg(p.group_scale_up + sg.group) : p.dequant_scale_up;
       // stream-K owner: the workers after this one hold the rest of this tile's K range
       int n_contrib = 0;
       if (sg.role == SEG_OWNER) {
@@ -1106,7 +1135,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // tile (int8: 32 rows x 64 B, dense; 16-bit: 32 rows x 128 B, swizzled) and one TMA store per tile.
         const int g_first = 2 * half;
         if (g_first < ngroups) {
-          const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+          const uint32_t buf = stage_base + (gcount % EPI_NBUF) * EPI_BUF_BYTES;
           if (gcount >= EPI_NBUF) {
             if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
             __syncwarp();
@@ -1119,8 +1148,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr0 + g * UNIT_N + 32, r1);
             tmem_ld_wait();
             float vg[32], vu[32];
-            epilogue_values<FP8>(r0, vg, tile_col0 + g * UNIT_N, rs, p, p.dequant_scale);
-            epilogue_values<FP8>(r1, vu, tile_col0 + g * UNIT_N + 32, rs, p, p.dequant_scale_up);
+            epilogue_values<FP8>(r0, vg, tile_col0 + g * UNIT_N, rs, p, tile_scale);
+            epilogue_values<FP8>(r1, vu, tile_col0 + g * UNIT_N + 32, rs, p, tile_scale_up);
             uint32_t w[16];
             swiglu_dispatch(vg, vu, w, p);
             if (out16) {
@@ -1172,8 +1201,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr0 + g0 * UNIT_N + UNIT_N + c * 32, rb);
             tmem_ld_wait();
             float va[32], vb[32];
-            epilogue_values<FP8>(ra, va, colh + c * 32, rs, p);
-            epilogue_values<FP8>(rb, vb, colh + UNIT_N + c * 32, rs, p);
+            epilogue_values<FP8>(ra, va, colh + c * 32, rs, p, tile_scale);
+            epilogue_values<FP8>(rb, vb, colh + UNIT_N + c * 32, rs, p, tile_scale);
             uint32_t wa[16], wb[16];
             if (bf) rope_chunk<true>(va, vb, wa, wb, rot, cos_row + c * 4 * blk, sin_row + c * 4 * blk, blk, p.rope_halves_equal != 0);
             else    rope_chunk<false>(va, vb, wa, wb, rot, cos_row + c * 4 * blk, sin_row + c * 4 * blk, blk, p.rope_halves_equal != 0);
@@ -1279,7 +1308,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (staged && out16) {
           // 64 output columns (two TMEM chunks) fill one 128-byte wide staging tile
-          const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+          const uint32_t buf = stage_base + (gcount % EPI_NBUF) * EPI_BUF_BYTES;
           if (gcount >= EPI_NBUF) {  // the store that last used this buffer must have read it
             if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
             __syncwarp();
@@ -1287,10 +1316,10 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
           float v[32];
           uint32_t w[16];
-          epilogue_values<FP8>(r0, v, col0, rs, p);
+          epilogue_values<FP8>(r0, v, col0, rs, p, tile_scale);
           pack_out16(v, w, p.y_dtype == ASQ_BF16);
           stage_words<16>(buf, lane, 0, w);
-          epilogue_values<FP8>(r1, v, col0 + 32, rs, p);
+          epilogue_values<FP8>(r1, v, col0 + 32, rs, p, tile_scale);
           pack_out16(v, w, p.y_dtype == ASQ_BF16);
           stage_words<16>(buf, lane, 4, w);
           fence_proxy_async_smem();
@@ -1306,7 +1335,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint32_t buf = stage_base + (gcount & 1u) * EPI_BUF_BYTES;
+            const uint32_t buf = stage_base + (gcount % EPI_NBUF) * EPI_BUF_BYTES;
             if (gcount >= EPI_NBUF) {
               if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
               __syncwarp();
@@ -1317,7 +1346,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             } else {
               float v[32];
               uint32_t w[32];
-              epilogue_values<FP8>(h ? r1 : r0, v, c0, rs, p);
+              epilogue_values<FP8>(h ? r1 : r0, v, c0, rs, p, tile_scale);
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 w[j] = (p.y_dtype == ASQ_I32) ? static_cast<uint32_t>(__float2int_rn(v[j])) : __float_as_uint(v[j]);
@@ -1704,7 +1733,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     static int mc_env = -1;
     if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     const int want = mc_env ? mc_env : 1;
-    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1) {
+    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr) {
       const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
       const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
       if (clusters > 0 && super_tiles >= clusters) mc = 2;
@@ -1713,6 +1742,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   }
   const int max_workers = (mc == 2) ? mc_clusters : st->sm_count / cg;
   p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
+  p.tile_m_blocks = cg;
   p.n_units = (p.N + asq::UNIT_N - 1) / asq::UNIT_N;
   p.num_k_blocks = (p.K + asq::BLOCK_K - 1) / asq::BLOCK_K;
   // Tile width in 64-column units.  Narrower tiles for decode-sized problems were measured slower on B200
@@ -1724,7 +1754,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (tu_env < 0) { const char* e = getenv("ASQ_TILE_UNITS"); tu_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     if (mc == 2) {
       p.tile_units = 2 * asq::TILE_N / asq::UNIT_N;  // the walk hands out 512-wide super tiles, one half per pair
-    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1) {
+    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr) {
       p.tile_units = tu_env;
     } else {
       // Wave quantisation: pick 256- or 192-column tiles, whichever needs less (rounds x width); 192-wide tiles
@@ -1797,9 +1827,10 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   CUtensorMap tmA, tmB, tmBu;
   rc = make_tmap(&tmA, a8, p.M, p.K, mc == 2 ? asq::BLOCK_M / 2 : asq::BLOCK_M);
   if (rc != ASQ_OK) return rc;
-  rc = make_tmap(&tmB, w, p.N, p.K, asq::TILE_N / cg);
+  const int64_t w_rows = static_cast<int64_t>(p.N) * (p.num_groups > 0 ? p.num_groups : 1);  // grouped: stacked expert weights
+  rc = make_tmap(&tmB, w, w_rows, p.K, asq::TILE_N / cg);
   if (rc != ASQ_OK) return rc;
-  rc = make_tmap(&tmBu, w, p.N, p.K, asq::UNIT_N / cg);
+  rc = make_tmap(&tmBu, w, w_rows, p.K, asq::UNIT_N / cg);
   if (rc != ASQ_OK) return rc;
   // Output map: y viewed as bytes [M, N*elem]; 32-row x 128-byte boxes (one epilogue warp's staging tile).
   CUtensorMap tmY;
@@ -2003,6 +2034,50 @@ int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const in
   p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
   p.row_scale = const_cast<float*>(row_scale);
   return launch_linear(false, xq, w_il, p, static_cast<cudaStream_t>(stream));
+}
+
+// ---- grouped (MoE expert) linear: one launch for all experts
+int asq_w8a8_grouped_linear(const void* x, int x_dtype, const int8_t* w_stacked, void* y, int y_dtype,
+                            int64_t M_pad, int64_t N, int64_t K, int num_groups, const int32_t* group_of_blk,
+                            const float* group_dequant_scale, const float* group_dequant_scale_up,
+                            const float* group_quant_scale, int act_mode, float* row_scale_out, int swiglu,
+                            int div_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, w_stacked, y, M_pad, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (!is_float_dtype(x_dtype)) return fail(ASQ_ERR_INVALID, "grouped: x dtype must be f32, f16 or bf16");
+  if (num_groups < 1 || num_groups > 4096 || group_of_blk == nullptr || group_dequant_scale == nullptr)
+    return fail(ASQ_ERR_INVALID, "grouped: need 1..4096 groups, the block->group table and the per-group dequant scales");
+  if (M_pad % asq::BLOCK_M != 0) return fail(ASQ_ERR_INVALID, "grouped: M_pad=%lld must be a multiple of 128 (segments padded to 256 rows)", (long long)M_pad);
+  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN)
+    return fail(ASQ_ERR_INVALID, "grouped: act_mode must be ROUND, SCALE or PER_TOKEN");
+  if (act_mode == ASQ_ACT_SCALE && group_quant_scale == nullptr) return fail(ASQ_ERR_INVALID, "grouped: ASQ_ACT_SCALE needs group_quant_scale");
+  if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
+  if (swiglu) {
+    if (N % 64 != 0) return fail(ASQ_ERR_INVALID, "grouped swiglu: N=%lld (2 x intermediate) must be a multiple of 64", (long long)N);
+    if (y_dtype != ASQ_BF16 && y_dtype != ASQ_F16) return fail(ASQ_ERR_INVALID, "grouped swiglu: y dtype must be f16 or bf16");
+    if (group_dequant_scale_up == nullptr) return fail(ASQ_ERR_INVALID, "grouped swiglu: need the up projections' scales");
+  } else {
+    if (!is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "grouped: y dtype must be f32, f16 or bf16");
+    if ((N * (y_dtype == ASQ_F32 ? 4 : 2)) % 16 != 0) return fail(ASQ_ERR_INVALID, "grouped: output rows must be 16-byte multiples");
+  }
+  if (M_pad == 0) return ASQ_OK;
+  if (workspace == nullptr || workspace_bytes < asq_workspace_bytes(M_pad, K))
+    return fail(ASQ_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", asq_workspace_bytes(M_pad, K), workspace_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(ASQ_ERR_INVALID, "workspace must be 1024-byte aligned");
+  Workspace ws;
+  ws_layout(M_pad, K, workspace, &ws);
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.sync = ws.sync;  // no stream-K in grouped launches
+  p.row_scale_out = row_scale_out;
+  p.quant_scale = 1.f; p.inv_quant_scale = 1.f; p.qmax = 127.0f; p.inv_qmax = 1.0f / 127.0f;
+  p.y = y; p.dequant_scale = 1.f; p.dequant_scale_up = 1.f;
+  p.M = static_cast<int>(M_pad); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.x_dtype = x_dtype; p.y_dtype = y_dtype; p.mid_dtype = y_dtype; p.act_mode = act_mode; p.div_mode = div_mode;
+  p.epi_kind = swiglu ? asq::EPI_SWIGLU : asq::EPI_DEQUANT;
+  p.group_of_blk = group_of_blk; p.group_scale = group_dequant_scale; p.group_scale_up = group_dequant_scale_up;
+  p.group_quant_scale = group_quant_scale; p.num_groups = num_groups;
+  return launch_linear(false, ws.a_q, w_stacked, p, static_cast<cudaStream_t>(stream));
 }
 
 // ---- row-parallel GEMM fused with its all-reduce over peer memory

@@ -179,6 +179,23 @@ int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const in
                               float gate_dequant_scale, float up_dequant_scale, const float* col_scale_il,
                               float out_quant_scale, int div_mode, void* stream);
 
+/* ---- Grouped linear: all experts of a Mixtral sparse-MoE block in ONE launch.
+ * Replaces the per-expert loop of HF MixtralSparseMoeBlock.forward (borrowed at models/mixtral.py:145) over
+ * Int8MixtralBlockSparseTop2MLP (models/mixtral.py:94-121): the caller sorts the routed token rows by expert
+ * into x [M_pad, K], padding every expert's segment with zero rows to a multiple of 256; group_of_blk[i]
+ * (device, int32) names the expert of rows [128 i, 128 i + 128), -1 for unused trailing blocks (skipped).
+ *   w_stacked [G * N, K] int8: expert g's weight in rows [g N, (g+1) N); group_dequant_scale [G] (device fp32)
+ *   act_mode ROUND | SCALE (per-expert group_quant_scale [G], LinearWithQuantScale) | PER_TOKEN
+ *   swiglu != 0: w_stacked holds every expert's w1|w3 in the interleaved layout of asq_w8a8_gateup_swiglu_q8
+ *   (N = 2 * ffn), group_dequant_scale / _up are the w1 / w3 scales, y [M_pad, N/2] = T(T(silu(w1 x)) * w3 x).
+ * Row results are independent of the other rows, so every real row equals what the expert's own module
+ * returns for that token, bit for bit. */
+int asq_w8a8_grouped_linear(const void* x, int x_dtype, const int8_t* w_stacked, void* y, int y_dtype,
+                            int64_t M_pad, int64_t N, int64_t K, int num_groups, const int32_t* group_of_blk,
+                            const float* group_dequant_scale, const float* group_dequant_scale_up,
+                            const float* group_quant_scale, int act_mode, float* row_scale_out, int swiglu,
+                            int div_mode, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Row-parallel linear fused with its all-reduce over NVLink peer memory (SURVEY 8(e) "fusion target").
  * One launch per rank replaces asq_w8a8_linear_q8 + ncclAllReduce(sum): every rank computes all output tiles
  * over its K shard; tile t is owned by rank t % world; non-owners store their raw int32 accumulators into the
