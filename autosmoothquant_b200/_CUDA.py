@@ -49,3 +49,19 @@ class I8CUGEMM:
         out = torch.empty((input.shape[0], weight.shape[0]), dtype=torch.int8, device=input.device)
         _lib.i8gemm_epi(input, weight, out, alpha, beta, bias=bias.reshape(-1).contiguous())
         return out
+
+
+# ---- csrc/kernels/bmm.cu (exported by the reference's legacy `_CUDA` build, used by layers/nn/bmm.py)
+def bmm_s8t_s8n_s8t(a: torch.Tensor, b: torch.Tensor, alpha: float) -> torch.Tensor:
+    """int8 [B,M,N] = sat(rint(alpha * a[B,M,K] @ b[B,N,K]^T))  (bmm.cu:82-148, LinearCombinationClamp)."""
+    return _lib.i8bmm(a, b, torch.int8, alpha)
+
+
+def bmm_s8t_s8n_f32t(a: torch.Tensor, b: torch.Tensor, alpha: float) -> torch.Tensor:
+    """float32 [B,M,N] = alpha * a @ b^T  (bmm.cu:10-80)."""
+    return _lib.i8bmm(a, b, torch.float32, alpha)
+
+
+def bmm_s8t_s8n_s32t(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """int32 [B,M,N] = a @ b^T, exact  (bmm.cu:150-211)."""
+    return _lib.i8bmm(a, b, torch.int32, 1.0)

@@ -29,7 +29,7 @@ def install_as_autosmoothquant(force: bool = False) -> None:
     from . import _CUDA, layers
     from .layers import functional, nn
     from .layers.functional import quantization
-    from .layers.nn import linear
+    from .layers.nn import bmm, linear
 
     if "autosmoothquant" not in sys.modules or force:
         try:
@@ -44,6 +44,7 @@ def install_as_autosmoothquant(force: bool = False) -> None:
         "autosmoothquant.layers": layers,
         "autosmoothquant.layers.nn": nn,
         "autosmoothquant.layers.nn.linear": linear,
+        "autosmoothquant.layers.nn.bmm": bmm,
         "autosmoothquant.layers.functional": functional,
         "autosmoothquant.layers.functional.quantization": quantization,
     }

@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = (
     "asq_w8a8_gateup_swiglu_q8",
     "asq_w8a8_linear_q8_rope",
     "asq_w8a8_grouped_linear",
+    "asq_i8bmm",
     "asq_ar_buffer_bytes",
     "asq_w8a8_linear_q8_allreduce",
     "asq_dev_alloc",
@@ -129,6 +130,8 @@ def load():
         lib.asq_w8a8_linear_q8_rope.restype = c_i
         lib.asq_w8a8_linear_q8_rope.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
                                                 c_vp, c_vp, c_i64, c_i64, c_i64, c_i, c_vp]
+        lib.asq_i8bmm.restype = c_i
+        lib.asq_i8bmm.argtypes = [c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i64, c_f, c_vp]
         lib.asq_w8a8_grouped_linear.restype = c_i
         lib.asq_w8a8_grouped_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_vp, c_vp, c_vp, c_vp,
                                                 c_i, c_vp, c_i, c_i, c_vp, c_sz, c_vp]
@@ -516,6 +519,27 @@ def w8a8_gateup_swiglu(
     _check(rc)
     _launches += 1
     return out
+
+
+def i8bmm(a: torch.Tensor, b: torch.Tensor, out_dtype: torch.dtype, alpha: float = 1.0) -> torch.Tensor:
+    """c[B,M,N] = epilogue(alpha * a[B,M,K] @ b[B,N,K]^T): int32 raw, float32 scaled, or int8 rounded + saturated."""
+    global _launches
+    dev = _require_cuda(a, b)
+    if a.dtype != torch.int8 or b.dtype != torch.int8 or a.dim() != 3 or b.dim() != 3 or a.shape[0] != b.shape[0] or a.shape[2] != b.shape[2]:
+        raise ValueError("i8bmm expects int8 a [B,M,K] and b [B,N,K]")
+    if out_dtype not in (torch.int8, torch.int32, torch.float32):
+        raise ValueError("i8bmm output dtype must be int8, int32 or float32")
+    a, b = a.contiguous(), b.contiguous()
+    B, M, K = a.shape
+    N = b.shape[1]
+    c = torch.empty((B, M, N), dtype=out_dtype, device=dev)
+    if B * M * N == 0:
+        return c
+    with torch.cuda.device(dev):
+        rc = load().asq_i8bmm(a.data_ptr(), b.data_ptr(), c.data_ptr(), _code(out_dtype), B, M, N, K, float(alpha), _stream(dev))
+    _check(rc)
+    _launches += 1
+    return c
 
 
 def w8a8_grouped_linear(

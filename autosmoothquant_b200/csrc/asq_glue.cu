@@ -19,10 +19,34 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 
 #include "../../include/asq.h"
 
 int asq_glue_fail(int code, const char* fmt, ...);  // defined in asq_kernels.cu (shares the error buffer)
+bool asq_pdl_enabled();                             // defined in asq_kernels.cu (ASQ_PDL=0 disables)
+
+// programmatic dependent launch (see asq_ptx.cuh): trigger the successor early, wait for the predecessor's results
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// <<<grid, block, 0, stream>>> with the programmatic-serialization attribute
+template <typename... KArgs, typename... Args>
+cudaError_t pdl_launch(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(block), 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = asq_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 namespace asq_glue {
 
@@ -83,6 +107,7 @@ __global__ void __launch_bounds__(NORM_THREADS) add_rmsnorm_quant_kernel(const T
                                                                          T* __restrict__ h_out, int8_t* __restrict__ q_out,
                                                                          int M, int H, float eps) {
   __shared__ float warp_sums[NORM_THREADS / 32];
+  pdl_sync();
   const int row = blockIdx.x;
   const int nvec = H / 8;  // vectors per row
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
@@ -172,6 +197,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) silu_mul_quant_kernel(const T* __restrict__ gate_up, long long row_stride, int M, int I,
                                                              float quant_scale, float inv_quant_scale, int div_mode,
                                                              int8_t* __restrict__ q_out, T* __restrict__ a_out) {
+  pdl_sync();
   // 32-bit index arithmetic (the host checks M * I / 8 < 2^31): 64-bit divisions would dominate the loop
   const uint32_t vec_per_row = static_cast<uint32_t>(I) / 8u;
   const uint32_t total = static_cast<uint32_t>(M) * vec_per_row;
@@ -209,6 +235,7 @@ __global__ void __launch_bounds__(256) silu_mul_quant_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) rope_kernel(T* __restrict__ qk, long long row_stride, const T* __restrict__ cos_t,
                                                    const T* __restrict__ sin_t, int M, int S, int n_heads, int head_dim) {
+  pdl_sync();
   // 32-bit index arithmetic (the host checks the element count < 2^31)
   const uint32_t half_vecs = static_cast<uint32_t>(head_dim) / 16u;  // 16-byte vectors in half a head
   const uint32_t per_row = static_cast<uint32_t>(n_heads) * half_vecs;
@@ -272,17 +299,18 @@ int asq_add_rmsnorm_quant(const void* x, const void* delta, const void* weight, 
   const int grid = static_cast<int>(M);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define ASQ_NORM_LAUNCH(TT, NVV)                                                                                        \
-  add_rmsnorm_quant_kernel<TT, NVV><<<grid, NORM_THREADS, 0, st>>>(static_cast<const TT*>(x), static_cast<const TT*>(delta), \
-                                                                   static_cast<const TT*>(weight), static_cast<TT*>(x_out), \
-                                                                   static_cast<TT*>(h_out), q_out, (int)M, (int)H, eps)
+  launch_err = pdl_launch(add_rmsnorm_quant_kernel<TT, NVV>, grid, NORM_THREADS, st, static_cast<const TT*>(x),            \
+                          static_cast<const TT*>(delta), static_cast<const TT*>(weight), static_cast<TT*>(x_out),         \
+                          static_cast<TT*>(h_out), q_out, (int)M, (int)H, eps)
   const int nv = static_cast<int>((H / 8 + NORM_THREADS - 1) / NORM_THREADS);
+  cudaError_t launch_err = cudaSuccess;
   if (dtype == ASQ_BF16) {
     if (nv <= 2) ASQ_NORM_LAUNCH(__nv_bfloat16, 2); else if (nv <= 4) ASQ_NORM_LAUNCH(__nv_bfloat16, 4); else ASQ_NORM_LAUNCH(__nv_bfloat16, 8);
   } else {
     if (nv <= 2) ASQ_NORM_LAUNCH(__half, 2); else if (nv <= 4) ASQ_NORM_LAUNCH(__half, 4); else ASQ_NORM_LAUNCH(__half, 8);
   }
 #undef ASQ_NORM_LAUNCH
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_err != cudaSuccess ? launch_err : cudaGetLastError();
   return e == cudaSuccess ? ASQ_OK : asq_glue_fail(ASQ_ERR_CUDA, "rmsnorm launch failed: %s", cudaGetErrorString(e));
 }
 

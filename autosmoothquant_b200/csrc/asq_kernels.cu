@@ -104,6 +104,7 @@ struct LinearParams {
   const float* group_scale_up;
   const float* group_quant_scale;
   int num_groups;
+  int batch_rows;  // batched GEMM: group = row / batch_rows (no table); rows per batch, a multiple of the tile height
   // Row-parallel GEMM fused with its all-reduce over peer memory (NVLink P2P): every rank computes the partial
   // of every tile over its K shard; tile t is OWNED by rank t % world.  Non-owners push their raw int32 / fp32
   // accumulators into the owner's receive buffer and raise a flag; the owner adds them to its own accumulator
@@ -804,7 +805,8 @@ struct TileWalk {
       sg.role = (owner == p.ar_rank) ? SEG_AR_OWNER : SEG_AR_CONTRIB;
     }
     tile_coords(t, p, sg.m_blk, n_blk);
-    sg.group = (p.group_of_blk != nullptr) ? __ldg(p.group_of_blk + sg.m_blk * p.tile_m_blocks) : 0;
+    sg.group = (p.group_of_blk != nullptr) ? __ldg(p.group_of_blk + sg.m_blk * p.tile_m_blocks)
+               : (p.batch_rows > 0 ? (sg.m_blk * p.tile_m_blocks * BLOCK_M) / p.batch_rows : 0);
     const int U = p.tile_units;  // tile width in 64-column units: 4, or fewer for decode-sized problems
     sg.col0 = n_blk * U * UNIT_N;
     sg.width = min(U, p.n_units - n_blk * U) * UNIT_N;
@@ -937,6 +939,10 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CG * MC > 1) cluster_sync_all(); else __syncthreads();  // peer barriers must exist before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // barriers, TMEM and descriptors are set up: let the next kernel of the stream start ITS set-up on SMs we
+  // free, and wait for our predecessor's results before touching global memory
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) ASQ_STAMP(1);
 
   if (warp == 0) {
@@ -1431,6 +1437,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Stand-alone prologue (debug / parity tap): same row routine, no GEMM.
 template <bool FP8>
 __global__ void __launch_bounds__(256) asq_quantize_kernel(const LinearParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < p.M; row += warps_total) {
@@ -1442,6 +1450,7 @@ __global__ void __launch_bounds__(256) asq_quantize_kernel(const LinearParams p)
 }  // namespace asq
 
 int asq_glue_fail(int code, const char* fmt, ...);  // formats into the thread-local error buffer (host TU)
+bool asq_pdl_enabled();                             // ASQ_PDL=0 turns programmatic dependent launch off (host TU)
 
 #if !defined(ASQ_TU) || ASQ_TU == 0
 // ====================================================================== host side
@@ -1458,6 +1467,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 }  // namespace
+
+bool asq_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ASQ_PDL"); on = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
 
 // error reporting shared with asq_glue.cu
 int asq_glue_fail(int code, const char* fmt, ...) {
@@ -1605,13 +1620,15 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   cfg.blockDim = dim3(asq::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG * MC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = asq_pdl_enabled() ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBu, tmY, tmPeers, p);
   if (e != cudaSuccess) return asq_glue_fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
@@ -1733,7 +1750,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     static int mc_env = -1;
     if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     const int want = mc_env ? mc_env : 1;
-    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr) {
+    if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr && p.batch_rows == 0) {
       const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
       const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
       if (clusters > 0 && super_tiles >= clusters) mc = 2;
@@ -1754,7 +1771,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (tu_env < 0) { const char* e = getenv("ASQ_TILE_UNITS"); tu_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     if (mc == 2) {
       p.tile_units = 2 * asq::TILE_N / asq::UNIT_N;  // the walk hands out 512-wide super tiles, one half per pair
-    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr) {
+    } else if (tu_env && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr && p.batch_rows == 0) {
       p.tile_units = tu_env;
     } else {
       // Wave quantisation: pick 256- or 192-column tiles, whichever needs less (rounds x width); 192-wide tiles
@@ -2036,6 +2053,43 @@ int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const in
   return launch_linear(false, xq, w_il, p, static_cast<cudaStream_t>(stream));
 }
 
+// ---- batched INT8 GEMM (csrc/kernels/bmm.cu): c[b] = epilogue(alpha * a[b] . w[b]^T)
+int asq_i8bmm(const int8_t* a, const int8_t* w, void* c, int c_dtype, int64_t batch, int64_t M, int64_t N, int64_t K,
+              float alpha, void* stream) {
+  if (batch < 0) return fail(ASQ_ERR_INVALID, "bmm: negative batch");
+  if (c_dtype != ASQ_I8 && c_dtype != ASQ_I32 && c_dtype != ASQ_F32) return fail(ASQ_ERR_INVALID, "bmm: output dtype must be i8, i32 or f32");
+  int rc = check_common(a, w, c, M, N, K);
+  if (rc != ASQ_OK || M == 0 || batch == 0) return rc;
+  if (batch * M > 0x7fffff00LL || batch * N > 0x7fffff00LL) return fail(ASQ_ERR_INVALID, "bmm: batch * rows too large");
+  const size_t elem = c_dtype == ASQ_I8 ? 1 : 4;
+  auto fill = [&](asq::LinearParams& p, void* y, int64_t rows) {
+    memset(&p, 0, sizeof(p));
+    p.y = y; p.M = static_cast<int>(rows); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+    p.y_dtype = c_dtype; p.act_mode = ASQ_ACT_ROUND;
+    if (c_dtype == ASQ_I32) { p.epi_kind = asq::EPI_RAW_I32; }           // bmm_s8t_s8n_s32t (alpha = 1)
+    else { p.epi_kind = asq::EPI_ALPHA_BETA; p.alpha = alpha; p.beta = 0.f; }  // _f32t: alpha*acc; _s8t: sat(rint(alpha*acc))
+  };
+  const int tile_m = asq::BLOCK_M * pick_cta_group(batch * M);
+  if (batch > 1 && M % tile_m == 0 && batch <= 65535) {
+    // every batch is a whole number of M tiles: ONE launch over the stacked [batch*M, K] x [batch*N, K] operands,
+    // the tile's batch index selects the weight rows (the grouped-GEMM path with group = row / M)
+    asq::LinearParams p;
+    fill(p, c, batch * M);
+    p.batch_rows = static_cast<int>(M);
+    p.num_groups = static_cast<int>(batch);
+    return launch_linear(false, a, w, p, static_cast<cudaStream_t>(stream));
+  }
+  for (int64_t b = 0; b < batch; ++b) {  // ragged M: one launch per batch entry
+    asq::LinearParams p;
+    fill(p, static_cast<uint8_t*>(c) + static_cast<size_t>(b) * M * N * elem, M);
+    if ((reinterpret_cast<uintptr_t>(p.y) & 15) || ((b * M * K) & 15) || ((b * N * K) & 15))
+      return fail(ASQ_ERR_INVALID, "bmm: per-batch matrices must stay 16-byte aligned (M*K, N*K, M*N*elem multiples of 16)");
+    rc = launch_linear(false, a + b * M * K, w + b * N * K, p, static_cast<cudaStream_t>(stream));
+    if (rc != ASQ_OK) return rc;
+  }
+  return ASQ_OK;
+}
+
 // ---- grouped (MoE expert) linear: one launch for all experts
 int asq_w8a8_grouped_linear(const void* x, int x_dtype, const int8_t* w_stacked, void* y, int y_dtype,
                             int64_t M_pad, int64_t N, int64_t K, int num_groups, const int32_t* group_of_blk,
@@ -2225,9 +2279,19 @@ int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale, int6
   long long blocks = (M + rows_per_block - 1) / rows_per_block;
   const long long cap = static_cast<long long>(st->sm_count) * 8;
   if (blocks > cap) blocks = cap;
-  if (fp8) asq::asq_quantize_kernel<true><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  else     asq::asq_quantize_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks), 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = asq_pdl_enabled() ? 1 : 0;
+  cudaError_t e = fp8 ? cudaLaunchKernelEx(&cfg, asq::asq_quantize_kernel<true>, p)
+                      : cudaLaunchKernelEx(&cfg, asq::asq_quantize_kernel<false>, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return ASQ_OK;
 }

@@ -236,6 +236,13 @@ int asq_i8gemm_epi(const int8_t* a, const int8_t* w, const void* bias, int bias_
                    float alpha, float beta, int flags, 
                    void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
+/* Batched INT8 GEMM, the csrc/kernels/bmm.cu family (bmm_s8t_s8n_{s8t,f32t,s32t}, layers/nn/bmm.py):
+ *   a [batch, M, K] int8 row-major, w [batch, N, K] int8 ("column-major B"), c [batch, M, N]
+ *   c_dtype ASQ_I32: raw accumulators (alpha ignored); ASQ_F32: alpha * f32(acc); ASQ_I8: sat_i8(rint(alpha * f32(acc))).
+ * One launch when M is a multiple of the tile height (256 rows; 128 when batch*M <= 128), else one per batch entry. */
+int asq_i8bmm(const int8_t* a, const int8_t* w, void* c, int c_dtype, int64_t batch, int64_t M, int64_t N, int64_t K,
+              float alpha, void* stream);
+
 /* Debug / parity tap of the fused prologue: writes the quantised activations
  * (int8, or e4m3 bytes when fp8 != 0) and, for per-token, the row scales. */
 int asq_quantize_act(const void* x, int x_dtype, void* q, float* row_scale,

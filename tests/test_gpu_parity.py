@@ -646,3 +646,33 @@ def test_config5_shapes_fp8_per_token(name, M, N, K):
     err = (y.double() - want).abs().max().item()
     # bf16 output rounding (2^-9 relative) + fp32 accumulation over K terms
     assert err <= want.abs().max().item() * (2 ** -8 + K * 2 ** -24), name
+
+
+# ----------------------------------------------------------------------------- batched INT8 GEMM (csrc/kernels/bmm.cu)
+@pytest.mark.parametrize("B,M,N,K", [(4, 256, 192, 128), (3, 512, 512, 64), (5, 100, 72, 48), (1, 300, 64, 32), (32, 256, 256, 128)])
+def test_i8bmm_family_vs_exact_integer_matmul(B, M, N, K):
+    """bmm_s8t_s8n_{s32t,f32t,s8t} (layers/nn/bmm.py, csrc/kernels/bmm.cu:10-211) against exact integer arithmetic:
+    int32 exact; float32 = fl(alpha * f32(acc)); int8 = sat(rint(that)).  M multiples of 256 take the one-launch
+    stacked path, the others one launch per batch entry."""
+    from autosmoothquant_b200.layers.nn.bmm import BMM_S8T_S8N_F32T, BMM_S8T_S8N_S8T, BMM_S8T_S8N_S32T
+
+    rng = np.random.default_rng(B * 1000 + M)
+    a = rng.integers(-128, 128, size=(B, M, K), dtype=np.int8)
+    b = rng.integers(-128, 128, size=(B, N, K), dtype=np.int8)
+    acc = np.einsum("bmk,bnk->bmn", a.astype(np.int64), b.astype(np.int64))
+    assert np.abs(acc).max() < 2 ** 31
+    before = L.launch_count()
+    got32 = BMM_S8T_S8N_S32T()(t(a), t(b))
+    assert L.launch_count() - before == 1
+    np.testing.assert_array_equal(got32.cpu().numpy(), acc.astype(np.int32))
+    alpha = np.float32(0.37 / (K * 40.0))
+    want_f = alpha * acc.astype(np.float32)  # int32 -> fp32 is exact here (|acc| < 2^24 for these K)
+    assert np.abs(acc).max() < 2 ** 24
+    got_f = BMM_S8T_S8N_F32T.from_scale(float(alpha), 1.0)(t(a), t(b))
+    assert got_f.dtype == torch.float32
+    np.testing.assert_array_equal(got_f.cpu().numpy(), want_f)
+    alpha8 = np.float32(1.0 / (K * 20.0))
+    want8 = np.clip(np.rint(alpha8 * acc.astype(np.float32)), -128, 127).astype(np.int8)
+    got8 = BMM_S8T_S8N_S8T(float(alpha8))(t(a), t(b))
+    assert got8.dtype == torch.int8 and int(np.abs(want8).max()) > 50
+    np.testing.assert_array_equal(got8.cpu().numpy(), want8)
