@@ -274,6 +274,17 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     tp_world = getattr(layer, "tp_world", 1)
     down = layer.down_proj.shard if tp_world > 1 else layer.down_proj
     il = getattr(layer, "gate_up_il", None)
+    if down.act_quant == "per-token":
+        # per-token fc2: the row absmax needs the whole SiLU*up row, so the epilogue emits the product in the
+        # activation dtype and down_proj (module / row-parallel wrapper) quantises it per token in its own launch
+        if il is not None:
+            a = _lib.w8a8_gateup_swiglu(q8, il[0], il[1], il[2], up_dequant_scale=il[3], out_quant_scale=None, mid_dtype=x2.dtype)
+        else:
+            gu_mod = layer.gate_up_proj
+            gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
+                                     col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
+            _, a = _lib.silu_mul_quant(gu, 1.0, want_q=False, want_a=True)
+        return x2, layer.down_proj(a)
     if il is not None:
         # SiLU(gate)*up and down_proj's activation quantisation run in the gate|up GEMM epilogue
         a8 = _lib.w8a8_gateup_swiglu(q8, il[0], il[1], il[2], up_dequant_scale=il[3],
@@ -307,9 +318,10 @@ class QuantDecoder(nn.Module):
         super().__init__()
         self.cfg = cfg
         self.qcfg = normalise_quant_config(quant_config or {})
-        # producer-side fusions need the fused projections and the all-per-tensor INT8 configuration
+        # producer-side fusions need the fused projections and per-tensor qkv / fc1 (the norm emits their int8 input);
+        # out / fc2 may be per-token (BASELINE config 3): those linears then quantise inside their own launch
         self.glue = bool(glue and fuse_projections and self.qcfg["type"] == "int8"
-                         and all(self.qcfg[k] == "per-tensor" for k in ("qkv", "out", "fc1", "fc2")))
+                         and all(self.qcfg[k] == "per-tensor" for k in ("qkv", "fc1")))
         self.dtype = dtype
         gen = torch.Generator(device=device).manual_seed(seed)
         n_layers = cfg.layers if layers is None else layers

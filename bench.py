@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
     ap.add_argument("--parallel", default="dp", choices=["dp", "tp"])
+    ap.add_argument("--quant", default="",
+                    help="quant_config overrides, e.g. 'out=per-token,fc2=per-token' (BASELINE config 3); default: all per-tensor")
     ap.add_argument("--tp-reduce", default="auto", choices=["auto", "fused", "nccl"],
                     help="--parallel tp: row-parallel GEMM fused with its all-reduce over peer memory (one launch), "
                          "or GEMM launch + NCCL all-reduce; auto = fused at 2 GPUs (measured faster), NCCL (NVLS) beyond")
@@ -177,8 +179,9 @@ def run_reference(args, cfg, layers):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": 1, "ms_per_step": t_layer * layers * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": f"{cfg.name} per-tensor INT8 prefill, batch {args.batch} x seq {args.seq}",
-                   "device": "host CPU", "layers": layers},
+        "config": {"workload": f"{cfg.name} prefill, {granularity_label(args)}, "
+                               f"batch {args.batch} x seq {args.seq} per GPU, bf16 activations",
+                   "device": "host CPU (oracle port of the quantized linears)", "layers": layers},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -230,6 +233,22 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def quant_overrides(args):
+    out = {}
+    for item in filter(None, (s.strip() for s in args.quant.split(","))):
+        key, _, val = item.partition("=")
+        out[key.strip()] = val.strip()
+    return out
+
+
+def granularity_label(args):
+    qc = {"qkv": "per-tensor", "out": "per-tensor", "fc1": "per-tensor", "fc2": "per-tensor"}
+    qc.update(quant_overrides(args))
+    if all(v == "per-tensor" for v in qc.values()):
+        return "all linears per-tensor INT8 (quant_config qkv/out/fc1/fc2=per-tensor)"
+    return "INT8, quant_config " + "/".join(f"{k}={qc[k]}" for k in ("qkv", "out", "fc1", "fc2"))
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args, cfg, layers):
     import torch
@@ -258,7 +277,7 @@ def run_ours(args, cfg, layers):
                                  fused_allreduce=args.tp_reduce == "fused", max_tokens=args.batch * world * args.seq)
         batch = args.batch * world  # weak scaling: the global batch grows with the GPU count
     else:
-        model = QuantDecoder(cfg, device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
+        model = QuantDecoder(cfg, quant_overrides(args), device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
                              fuse_projections=not args.no_fuse, glue=not args.no_glue)
         batch = args.batch
     B, S = batch, args.seq
@@ -440,7 +459,7 @@ def run_ours(args, cfg, layers):
             "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {
-                "workload": f"{cfg.name} prefill, all linears per-tensor INT8 (quant_config qkv/out/fc1/fc2=per-tensor), "
+                "workload": f"{cfg.name} prefill, {granularity_label(args)}, "
                             f"batch {args.batch} x seq {S} per GPU, bf16 activations",
                 "layers": layers, "global_batch": B * replicas, "seq_len": S,
                 "parallelism": f"{args.parallel}{world}", "cuda_graph": graph is not None,

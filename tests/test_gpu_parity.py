@@ -531,6 +531,22 @@ def test_glue_stack_swiglu_epilogue_is_bit_identical():
     assert torch.equal(a(ids, last_token_only=False), b(ids, last_token_only=False))
 
 
+def test_glue_stack_config3_per_token_out_fc2():
+    """BASELINE config 3 granularities (qkv / fc1 per-tensor, out / fc2 per-token): the producer-fused path keeps
+    the norm->int8 and SwiGLU-epilogue fusions and must agree with the module path like the all-per-tensor case."""
+    from autosmoothquant_b200 import harness
+
+    qc = {"qkv": "per-tensor", "out": "per-token", "fc1": "per-tensor", "fc2": "per-token"}
+    ids = torch.randint(0, harness.TINY.vocab, (2, 64), generator=torch.Generator().manual_seed(0)).to(DEV)
+    a = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=3, fuse_projections=True, glue=False)
+    b = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=3, fuse_projections=True, glue=True)
+    assert b.glue and not a.glue and b.layers[0].down_proj.act_quant == "per-token"
+    ya, yb = a(ids, last_token_only=False), b(ids, last_token_only=False)
+    assert torch.isfinite(yb).all() and float((ya - yb).abs().max()) <= 0.05 * float(ya.abs().max())
+    c = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=3, fuse_projections=True, glue=True, swiglu_epilogue=False)
+    assert torch.equal(yb, c(ids, last_token_only=False))  # SwiGLU epilogue (16-bit output) == separate SiLU kernel
+
+
 def test_glue_stack_close_to_module_stack():
     """Whole tiny decoder: producer-fused path vs module path.  Not bit-identical by construction (the fp32
     variance is summed in a different order), so compare logits with a tolerance."""
