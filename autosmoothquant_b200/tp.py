@@ -28,6 +28,7 @@ from torch import nn
 
 from . import _lib
 from .layers.nn.linear import (
+    FP8LinearDynamic,
     W8A8BFP32OFP32Linear,
     W8A8BFP32OFP32LinearWithQuantScale,
 )
@@ -40,9 +41,23 @@ def _shard_bounds(size: int, rank: int, world: int, align: int = 16):
     return rank * step, (rank + 1) * step
 
 
+def _shard_fp8(module: FP8LinearDynamic, rows: slice, cols: slice, keep_bias: bool) -> FP8LinearDynamic:
+    """FP8-e4m3 dynamic module (BASELINE config 5) restricted to weight[rows, cols]; the per-tensor weight scale is
+    shared by every shard, exactly as the INT8 dequant scale."""
+    w = module.weight.view(torch.uint8)[rows, cols].contiguous().view(torch.float8_e4m3fn)
+    out = FP8LinearDynamic(w.shape[1], w.shape[0], module.act_quant, keep_bias)
+    out.weight = w
+    out.weight_scale = module.weight_scale.clone()
+    if keep_bias:
+        out.bias = module.bias[rows].clone()
+    return out
+
+
 def shard_column(module: nn.Module, rank: int, world: int) -> nn.Module:
-    """Rank's column-parallel shard (rows [rN/p, (r+1)N/p) of the [N,K] weight) of an INT8 module."""
+    """Rank's column-parallel shard (rows [rN/p, (r+1)N/p) of the [N,K] weight) of an INT8 / FP8 module."""
     lo, hi = _shard_bounds(module.out_features, rank, world, align=1)
+    if isinstance(module, FP8LinearDynamic):
+        return _shard_fp8(module, slice(lo, hi), slice(None), module.use_bias)
     out = type(module)(module.in_features, hi - lo, module.use_bias, module.act_quant)
     out.weight = module.weight[lo:hi].contiguous()
     if module.use_bias:
@@ -56,6 +71,8 @@ def shard_row(module: nn.Module, rank: int, world: int) -> nn.Module:
     """Rank's row-parallel shard (columns [rK/p, (r+1)K/p) of the [N,K] weight); bias stays on rank 0."""
     lo, hi = _shard_bounds(module.in_features, rank, world, align=16)
     keep_bias = module.use_bias and rank == 0
+    if isinstance(module, FP8LinearDynamic):
+        return _shard_fp8(module, slice(None), slice(lo, hi), keep_bias)
     out = type(module)(hi - lo, module.out_features, keep_bias, module.act_quant)
     out.weight = module.weight[:, lo:hi].contiguous()
     if keep_bias:
@@ -101,6 +118,8 @@ class ColumnParallelLinear(nn.Module):
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.shard
+        if isinstance(m, FP8LinearDynamic):  # replicated input: the module's own fused launch, output stays sharded
+            return m(x)
         x2 = x.reshape(-1, m.in_features)
         if m.act_quant == "per-token":
             mode, qs = _lib.ACT_PER_TOKEN, 1.0
@@ -146,6 +165,8 @@ class RowParallelLinear(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.shard
         x2 = x.reshape(-1, m.in_features)
+        if isinstance(m, FP8LinearDynamic):
+            return self._forward_fp8(m, x, x2)
         row_scale = None
         if m.act_quant == "per-token":
             if self.local_scales:
@@ -185,6 +206,24 @@ class RowParallelLinear(nn.Module):
             y = y.float()
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
         return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
+
+
+def _rowparallel_forward_fp8(self, m: FP8LinearDynamic, x: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """FP8 per-token row-parallel (config 5): the per-token scale is absmax(row over the WHOLE K) / 448, so the local
+    scales are max-all-reduced and the kernel quantises with the supplied scales; fp32-accumulated partial
+    products are rounded to the activation dtype (or kept fp32, reduce="fp32") and summed by one all-reduce."""
+    if m.act_quant != "per-token" or self.reduce in ("int32", "fused"):
+        raise NotImplementedError("FP8 row-parallel: per-token activations with reduce='native' or 'fp32' only")
+    _, row_scale = _lib.quantize_act(x2, _lib.ACT_PER_TOKEN, fp8=True)
+    if not self.local_scales:
+        dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)
+    y = _lib.fp8_linear(x2, m.weight, m._bias_f32(), _lib.ACT_ROW_SCALE_GIVEN, 1.0, float(m.weight_scale.item()),
+                        out_dtype=torch.float32 if self.reduce == "fp32" else None, row_scale_out=row_scale)
+    dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+    return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
+
+
+RowParallelLinear._forward_fp8 = _rowparallel_forward_fp8
 
 
 def _shard_fused_columns(fused, rank: int, world: int, device):

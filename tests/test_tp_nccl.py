@@ -45,6 +45,20 @@ def _worker(rank, world, port, ret):
             row_n = tp.RowParallelLinear(tp.shard_row(full, rank, world).to(dev), reduce="native", has_bias=True)
             got_n = row_n(x[:, lo:hi].contiguous())
             results[f"native {act}"] = bool(torch.allclose(got_n.float(), want.float(), rtol=2 ** -6, atol=2 ** -6 * float(want.abs().max())))
+        # FP8-e4m3 per-token (BASELINE config 5): column- then row-parallel pair against the unsharded modules
+        from autosmoothquant_b200.layers.nn.linear import FP8LinearDynamic
+        lin1, lin2 = torch.nn.Linear(K, 1536, bias=False), torch.nn.Linear(1536, N, bias=True)
+        f1 = FP8LinearDynamic.from_float(lin1, act_quant="per-token")._apply(lambda t: t.to(dev))
+        f2 = FP8LinearDynamic.from_float(lin2, act_quant="per-token")._apply(lambda t: t.to(dev))
+        xf = x.float()  # the reference's fp8 path effectively runs in fp32
+        want = f2(f1(xf))
+        col = tp.ColumnParallelLinear(tp.shard_column(f1, rank, world)._apply(lambda t: t.to(dev)))
+        row = tp.RowParallelLinear(tp.shard_row(f2, rank, world)._apply(lambda t: t.to(dev)), reduce="fp32", has_bias=True)
+        h_local = col(xf)
+        lo, hi = rank * 1536 // world, (rank + 1) * 1536 // world
+        results["fp8 column shard == slice of the unsharded output"] = bool(torch.equal(h_local, f1(xf)[:, lo:hi]))
+        got = row(h_local)
+        results["fp8 row-parallel per-token"] = bool(torch.allclose(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max())))
         # decoder stack: TP (fused + producer kernels) vs single GPU
         ids = torch.randint(0, harness.TINY.vocab, (2, 64), generator=torch.Generator().manual_seed(0)).to(dev)
         ref = harness.QuantDecoder(harness.TINY, {}, device=dev, seed=3, fuse_projections=True, glue=True)(ids, last_token_only=False)
