@@ -140,7 +140,7 @@ def load():
         lib.asq_ar_buffer_bytes.argtypes = [c_i64, c_i64, c_i, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]
         lib.asq_w8a8_linear_q8_allreduce.restype = c_i
         lib.asq_w8a8_linear_q8_allreduce.argtypes = [c_vp, c_vp, c_vp, c_vp, c_pp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
-                                                     c_pp, c_pp, c_i, c_i, c_vp]
+                                                     c_pp, c_pp, c_i, c_i, c_i, c_vp, c_vp]
         lib.asq_dev_alloc.restype = c_i
         lib.asq_dev_alloc.argtypes = [c_sz, c_pp]
         lib.asq_dev_free.restype = c_i

@@ -114,6 +114,9 @@ struct LinearParams {
   // process; words: [0] epoch of the last finished launch, [1] CTAs finished, [2+s] "rank s finished launch e",
   // [64...] one arrival flag per (source slot, owned tile, CTA of the pair, epilogue warp).
   int ar_world, ar_rank, ar_tiles, ar_cnt_max;
+  int ar_partial16;    // 1: partials travel dequantised in the 16-bit output dtype (NCCL-native numerics, half the bytes)
+  uint8_t* ar_y_mc;    // != NULL: NVLS multicast address of the y buffers; finished tiles leave by multimem.st (one store
+                       // reaches every rank through the switch) instead of one TMA store per rank
   uint32_t* ar_ctl[8];
   uint32_t* ar_recv[8];
   int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
@@ -1250,6 +1253,25 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 8; ++q) __stcg(dst + (8 + q) * 32, make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]));
           continue;
         }
+        if (sg.role == SEG_AR_CONTRIB && p.ar_partial16) {
+          // dequantised partial (+ bias on the rank that holds it), rounded to the output dtype: 2 bytes per element
+          tmem_ld_wait();
+          const int owner = sg.ar_tile % p.ar_world;
+          const int slot = (p.ar_rank - owner - 1 + p.ar_world) % p.ar_world;
+          uint4* dst = reinterpret_cast<uint4*>(p.ar_recv[owner] + ar_index(p, slot, sg.ar_tile / p.ar_world, CG, cta_rank, ew) * SK_WARP_WORDS) +
+                       chunk_pair * 8 * 32 + lane;
+          float v[32];
+          uint32_t w[16];
+          epilogue_values<FP8>(r0, v, col0, rs, p, tile_scale);
+          pack_out16(v, w, p.y_dtype == ASQ_BF16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q * 32] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          epilogue_values<FP8>(r1, v, col0 + 32, rs, p, tile_scale);
+          pack_out16(v, w, p.y_dtype == ASQ_BF16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[(4 + q) * 32] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          continue;
+        }
         if (sg.role == SEG_AR_CONTRIB) {
           // raw partial accumulators -> the owner's receive buffer over NVLink, coalesced 512-byte warp stores
           tmem_ld_wait();
@@ -1263,7 +1285,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 8; ++q) dst[(8 + q) * 32] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
           continue;
         }
-        if (sg.role == SEG_AR_OWNER) {
+        if (sg.role == SEG_AR_OWNER && !p.ar_partial16) {
           tmem_ld_wait();
           for (int sl = 0; sl < p.ar_world - 1; ++sl) {  // fixed source order: deterministic fp32 sums
             const uint4* src = reinterpret_cast<const uint4*>(p.ar_recv[p.ar_rank] + ar_index(p, sl, sg.ar_tile / p.ar_world, CG, cta_rank, ew) * SK_WARP_WORDS) +
@@ -1322,18 +1344,63 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
           float v[32];
           uint32_t w[16];
-          epilogue_values<FP8>(r0, v, col0, rs, p, tile_scale);
-          pack_out16(v, w, p.y_dtype == ASQ_BF16);
-          stage_words<16>(buf, lane, 0, w);
-          epilogue_values<FP8>(r1, v, col0 + 32, rs, p, tile_scale);
-          pack_out16(v, w, p.y_dtype == ASQ_BF16);
-          stage_words<16>(buf, lane, 4, w);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && row0 < p.M && col0 < p.N) {
-            tma_store_2d(&tmY, buf, col0 * elem, row0);
-            for (int pr = 0; pr < p.ar_world - 1; ++pr) tma_store_2d(&tmPeers.m[pr], buf, col0 * elem, row0);  // all-gather by stores
-            tma_store_commit();
+          const bool ar16_owner = (sg.role == SEG_AR_OWNER && p.ar_partial16);
+          const bool bf_out = (p.y_dtype == ASQ_BF16);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            epilogue_values<FP8>(h ? r1 : r0, v, col0 + h * 32, rs, p, tile_scale);
+            if (ar16_owner) {
+              // own partial rounded to the output dtype like everybody's, then the peers' 16-bit partials added in
+              // fp32 in fixed source order; one final rounding in pack_out16 (world 2: exactly NCCL's bf16 sum)
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                if (bf_out) round_pair<true>(v[j], v[j + 1]); else round_pair<false>(v[j], v[j + 1]);
+              }
+              for (int sl = 0; sl < p.ar_world - 1; ++sl) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.ar_recv[p.ar_rank] + ar_index(p, sl, sg.ar_tile / p.ar_world, CG, cta_rank, ew) * SK_WARP_WORDS) +
+                                   chunk_pair * 8 * 32 + h * 4 * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 a = __ldcg(src + q * 32);
+                  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float lo, hi;
+                    if (bf_out) unpack_pair<true>(aw[i], lo, hi); else unpack_pair<false>(aw[i], lo, hi);
+                    v[8 * q + 2 * i] = __fadd_rn(v[8 * q + 2 * i], lo);
+                    v[8 * q + 2 * i + 1] = __fadd_rn(v[8 * q + 2 * i + 1], hi);
+                  }
+                }
+              }
+            }
+            pack_out16(v, w, bf_out);
+            stage_words<16>(buf, lane, h * 4, w);
+          }
+          if (p.ar_y_mc != nullptr && sg.role == SEG_AR_OWNER) {
+            // NVLS: read the staged tile back row-major (8 lanes x 16 bytes = one 128-byte row) and multicast it
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3), c = lane & 7;
+              uint32_t x0, x1, x2, x3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                           : "r"(buf + r * 128 + ((c ^ (r & 7)) << 4)));
+              const int grow = row0 + r, gcol = col0 + c * 8;
+              if (grow < p.M && gcol < p.N) {
+                uint8_t* dst = p.ar_y_mc + (static_cast<size_t>(grow) * p.N + gcol) * 2;
+                asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(x0)),
+                             "f"(__uint_as_float(x1)), "f"(__uint_as_float(x2)), "f"(__uint_as_float(x3)) : "memory");
+              }
+            }
+            __syncwarp();  // the buffer may be rewritten by the next group: every lane has read its part
+          } else {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && col0 < p.N) {
+              tma_store_2d(&tmY, buf, col0 * elem, row0);
+              for (int pr = 0; pr < p.ar_world - 1; ++pr) tma_store_2d(&tmPeers.m[pr], buf, col0 * elem, row0);  // all-gather by stores
+              tma_store_commit();
+            }
           }
           ++gcount;
         } else if (staged) {
@@ -2151,7 +2218,8 @@ int asq_ar_buffer_bytes(int64_t M, int64_t N, int world, size_t* recv_bytes, siz
 int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
                                  void* const* y_all, int y_dtype, int64_t M, int64_t N, int64_t K,
                                  float dequant_scale, const float* col_scale, void* const* recv_all,
-                                 void* const* ctl_all, int rank, int world, void* stream) {
+                                 void* const* ctl_all, int rank, int world, int partial16, void* y_multicast,
+                                 void* stream) {
   if (world < 2 || world > 8 || rank < 0 || rank >= world || y_all == nullptr || recv_all == nullptr || ctl_all == nullptr)
     return fail(ASQ_ERR_INVALID, "allreduce: bad rank %d / world %d or null pointer tables", rank, world);
   for (int r = 0; r < world; ++r)
@@ -2171,6 +2239,10 @@ int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const
   p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
   p.row_scale = const_cast<float*>(row_scale);
   p.ar_world = world; p.ar_rank = rank;
+  p.ar_partial16 = partial16 ? 1 : 0;
+  p.ar_y_mc = static_cast<uint8_t*>(y_multicast);
+  if (y_multicast != nullptr && (reinterpret_cast<uintptr_t>(y_multicast) & 15))
+    return fail(ASQ_ERR_INVALID, "allreduce: the multicast address must be 16-byte aligned");
   void* peers[7];
   int n = 0;
   for (int r = 0; r < world; ++r) {

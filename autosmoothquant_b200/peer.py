@@ -33,7 +33,7 @@ class _DevBuffer:
 
 class PeerComm:
     def __init__(self, group=None, device: Optional[torch.device] = None, max_m: int = 2048, max_n: int = 8192,
-                 dtype: torch.dtype = torch.bfloat16):
+                 dtype: torch.dtype = torch.bfloat16, multicast: bool = False):
         if not dist.is_initialized():
             raise RuntimeError("PeerComm needs an initialised torch.distributed process group")
         self.group = group
@@ -48,7 +48,22 @@ class PeerComm:
         with torch.cuda.device(self.device):
             _lib._check(lib.asq_ar_buffer_bytes(self.max_m, self.max_n, self.world, ctypes.byref(recv_b), ctypes.byref(ctl_b)))
             y_bytes = self.max_m * self.max_n * 2
-            sizes = {"recv": recv_b.value, "ctl": ctl_b.value, "y0": y_bytes, "y1": y_bytes}
+            sizes = {"recv": recv_b.value, "ctl": ctl_b.value}
+            self._symm = None
+            self.multicast_ptr = 0
+            if multicast:
+                # the output buffers live in torch symmetric memory so that an NVLS multicast address exists for them
+                import torch.distributed._symmetric_memory as symm
+
+                self._symm_tensor = symm.empty(2 * y_bytes, dtype=torch.uint8, device=self.device)
+                self._symm_tensor.zero_()
+                pg = dist.group.WORLD if group is None else group
+                self._symm = symm.rendezvous(self._symm_tensor, pg.group_name)
+                if not self._symm.multicast_ptr:
+                    raise RuntimeError("this system exposes no NVLS multicast address (multicast=True needs NVSwitch)")
+                self.multicast_ptr = int(self._symm.multicast_ptr)
+            else:
+                sizes.update({"y0": y_bytes, "y1": y_bytes})
             self._own = {}
             handles = {}
             for name, nbytes in sizes.items():
@@ -73,16 +88,27 @@ class PeerComm:
                         _lib._check(lib.asq_ipc_open(buf, ctypes.byref(out)))
                         self._opened.append(out.value)
                         self.ptrs[name][r] = out.value
-        self._tables = {name: (ctypes.c_void_p * self.world)(*self.ptrs[name]) for name in sizes}
-        self._y_views = [torch.as_tensor(_DevBuffer(*self._own[n]), device=self.device) for n in ("y0", "y1")]
+        if self._symm is not None:
+            base = [int(p) for p in self._symm.buffer_ptrs]
+            self.ptrs["y0"] = base
+            self.ptrs["y1"] = [b + y_bytes for b in base]
+            self._y_views = [self._symm_tensor[:y_bytes], self._symm_tensor[y_bytes:]]
+        else:
+            self._y_views = [torch.as_tensor(_DevBuffer(*self._own[n]), device=self.device) for n in ("y0", "y1")]
+        self._y_bytes = y_bytes
+        self._tables = {name: (ctypes.c_void_p * self.world)(*self.ptrs[name]) for name in self.ptrs}
         self._launches = 0
         dist.barrier(group=group)  # every rank's buffers exist, are zeroed and mapped before the first launch
 
     def linear_q8_allreduce(self, xq: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                             dequant_scale: float, col_scale: Optional[torch.Tensor] = None,
-                            row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+                            row_scale: Optional[torch.Tensor] = None, partials: str = "int32") -> torch.Tensor:
         """sum over ranks of (xq_r . weight_r^T), dequantised (+ bias) — xq [M, K/world] int8, weight [N, K/world]
-        int8, bias on EVERY rank.  Returns a [M, N] view of this rank's symmetric output buffer."""
+        int8.  partials="int32": exact integer exchange, bias on EVERY rank, result bit-identical to the unsharded
+        module; partials="native": 16-bit dequantised partials (half the bytes, NCCL-native numerics), bias on ONE
+        rank only.  Returns a [M, N] view of this rank's symmetric output buffer."""
+        if partials not in ("int32", "native"):
+            raise ValueError("partials must be 'int32' or 'native'")
         if xq.dtype != torch.int8 or weight.dtype != torch.int8 or xq.dim() != 2 or xq.shape[1] != weight.shape[1]:
             raise ValueError("linear_q8_allreduce expects int8 [M,K] activations and int8 [N,K] weights")
         if not (xq.is_cuda and weight.is_cuda and xq.is_contiguous() and weight.is_contiguous()):
@@ -103,7 +129,8 @@ class PeerComm:
             rc = lib.asq_w8a8_linear_q8_allreduce(
                 xq.data_ptr(), _lib._ptr(row_scale), weight.data_ptr(), _lib._ptr(bias), y_table, _lib._code(self.dtype),
                 M, N, K, float(dequant_scale), _lib._ptr(col_scale), self._tables["recv"], self._tables["ctl"],
-                self.rank, self.world, _lib._stream(self.device))
+                self.rank, self.world, 1 if partials == "native" else 0,
+                (self.multicast_ptr + which * self._y_bytes) if self.multicast_ptr else None, _lib._stream(self.device))
         _lib._check(rc)
         _lib._launches += 1
         self._launches += 1

@@ -207,13 +207,20 @@ int asq_w8a8_grouped_linear(const void* x, int x_dtype, const int8_t* w_stacked,
  *       receive and control buffer (own buffers from asq_dev_alloc, the peers' via asq_ipc_open).  Sizes from
  *       asq_ar_buffer_bytes for the largest (M, N) used; zero-filled at allocation, never reset by the host.
  *   bias (fp32 [N]) must be given on EVERY rank (the tile owner applies it); row_scale = global per-token scales.
+ *   partial16 != 0: partials travel dequantised and rounded to y's 16-bit dtype instead (half the bytes; the
+ *       owner adds them in fp32 in fixed rank order and rounds once: at world 2 exactly the result of a bf16
+ *       ncclAllReduce of the per-rank outputs).  In this mode bias must be given on ONE rank only.
+ *   y_multicast != NULL: the NVLS multicast address bound to all ranks' y buffers (cuMulticast* / torch
+ *       symmetric memory); finished tiles are then broadcast with multimem.st — one store reaches every rank
+ *       through the switch — instead of one TMA store per peer.
  * Every rank of the group must issue the same sequence of these calls (same shapes); a launch returns only
  * after every peer has finished writing this rank's y.  y may be reused by the launch after the next one. */
 int asq_ar_buffer_bytes(int64_t M, int64_t N, int world, size_t* recv_bytes, size_t* ctl_bytes);
 int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
                                  void* const* y_all, int y_dtype, int64_t M, int64_t N, int64_t K,
                                  float dequant_scale, const float* col_scale, void* const* recv_all,
-                                 void* const* ctl_all, int rank, int world, void* stream);
+                                 void* const* ctl_all, int rank, int world, int partial16, void* y_multicast,
+                                 void* stream);
 /* Zero-filled cudaMalloc memory and CUDA IPC handles (64 bytes) to map it into the other ranks' processes. */
 int asq_dev_alloc(size_t bytes, void** ptr);
 int asq_dev_free(void* ptr);

@@ -77,6 +77,36 @@ def _worker(rank, world, port, ret):
             ok = ok and bool(torch.equal(got.clone(), want))
         torch.cuda.synchronize()
         results["20 launches back to back"] = ok
+        # 4. NVLS multicast broadcast of the finished tiles (multimem.st) and 16-bit ("native") partials
+        comm_mc = peer.PeerComm(device=dev, max_m=2048, max_n=4096, multicast=True)
+        for (M, N, K) in SHAPES[:3]:
+            a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+            w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(dev)
+            b = torch.randn(N, generator=g).to(dev)
+            rs = (torch.rand(M, generator=g) + 0.5).to(dev)
+            step = K // world // 16 * 16
+            lo, hi = rank * step, (K if rank == world - 1 else (rank + 1) * step)
+            al, wl = a[:, lo:hi].contiguous(), w[:, lo:hi].contiguous()
+            want = _lib.w8a8_linear_q8(a, w, b, 3e-5, row_scale=rs)
+            for c, tag in ((comm_mc, "multicast"), ):
+                got = c.linear_q8_allreduce(al, wl, b, 3e-5, row_scale=rs)
+                torch.cuda.synchronize()
+                results[f"{tag} int32 {M}x{N}x{K}"] = bool(torch.equal(got, want))
+            # native partials: what GEMM + bf16 ncclAllReduce computes (bias on rank 0 only)
+            y_nccl = _lib.w8a8_linear_q8(al, wl, b if rank == 0 else None, 3e-5, row_scale=rs)
+            dist.all_reduce(y_nccl)
+            for c, tag in ((comm, "p2p"), (comm_mc, "multicast")):
+                got = c.linear_q8_allreduce(al, wl, b if rank == 0 else None, 3e-5, row_scale=rs, partials="native")
+                torch.cuda.synchronize()
+                if world == 2:  # one fp32 add of two bf16 values, rounded once: identical to NCCL's sum
+                    results[f"{tag} native {M}x{N}x{K}"] = bool(torch.equal(got, y_nccl))
+                else:  # summation order differs from NCCL's: same value up to the bf16 rounding of the partial sums
+                    results[f"{tag} native {M}x{N}x{K}"] = bool(torch.allclose(got.float(), y_nccl.float(), rtol=2 ** -6,
+                                                                                 atol=2 ** -6 * float(want.float().abs().max())))
+                ranks_equal = [torch.empty_like(got) for _ in range(world)]
+                dist.all_gather(ranks_equal, got.clone())
+                results[f"{tag} native identical on all ranks {M}x{N}x{K}"] = all(bool(torch.equal(ranks_equal[0], r)) for r in ranks_equal)
+        comm_mc.close()
         comm.close()
     except Exception as e:  # noqa: BLE001
         results["exception"] = repr(e)
