@@ -297,8 +297,12 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     comm = getattr(layer, "peer_comm", None)
     if tp_world > 1 and comm is not None:
         # row-parallel GEMM + all-reduce in ONE launch over NVLink peer memory (exact int32 partial sums)
-        d = comm.linear_q8_allreduce(a8, down.weight, layer.down_proj._bias_everywhere(x2.device),
-                                     float(down.dequant_scale.item()))
+        if getattr(layer, "peer_partials", "int32") == "native":
+            d = comm.linear_q8_allreduce(a8, down.weight, down.bias if down.use_bias else None,
+                                         float(down.dequant_scale.item()), partials="native")
+        else:
+            d = comm.linear_q8_allreduce(a8, down.weight, layer.down_proj._bias_everywhere(x2.device),
+                                         float(down.dequant_scale.item()))
         return x2, d
     d = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
                             out_dtype=x2.dtype)

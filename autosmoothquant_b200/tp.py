@@ -140,9 +140,9 @@ class RowParallelLinear(nn.Module):
     def __init__(self, shard: nn.Module, group=None, reduce: str = "native", local_scales: bool = False,
                  backend=CudaBackend, has_bias: Optional[bool] = None, comm=None):
         super().__init__()
-        if reduce not in ("native", "fp32", "int32", "fused"):
-            raise ValueError("reduce must be 'native' (activation dtype), 'fp32', 'int32' or 'fused'")
-        if reduce == "fused" and comm is None:
+        if reduce not in ("native", "fp32", "int32", "fused", "fused-native"):
+            raise ValueError("reduce must be 'native' (activation dtype), 'fp32', 'int32', 'fused' or 'fused-native'")
+        if reduce.startswith("fused") and comm is None:
             raise ValueError("reduce='fused' needs a peer.PeerComm (GEMM + all-reduce in one kernel over peer memory)")
         self.comm = comm
         self.shard, self.group, self.reduce, self.local_scales, self.backend = shard, group, reduce, local_scales, backend
@@ -180,14 +180,19 @@ class RowParallelLinear(nn.Module):
         else:
             mode, qs = _lib.ACT_ROUND, 1.0
 
-        if self.reduce == "fused":
-            # ONE launch per rank, no NCCL: int32 partials over NVLink peer stores, owner-side exact sum and the
-            # unsharded module's fp32 epilogue, finished tiles stored into every rank's output (peer.PeerComm)
+        if self.reduce.startswith("fused"):
+            # ONE launch per rank, no NCCL (peer.PeerComm).  "fused": int32 partials over NVLink peer stores, exact
+            # owner-side sum, the unsharded module's fp32 epilogue -> bit-identical to the unsharded module.
+            # "fused-native": 16-bit dequantised partials (half the bytes) = the numerics of reduce="native".
             if mode == _lib.ACT_PER_TOKEN:
                 raise NotImplementedError("reduce='fused' needs global row scales (local_scales=False)")
             q, _ = _lib.quantize_act(x2, mode, qs, row_scale=row_scale)
-            y = self.comm.linear_q8_allreduce(q, m.weight, self._bias_everywhere(x2.device),
-                                              float(m.dequant_scale.item()), row_scale=row_scale)
+            if self.reduce == "fused":
+                y = self.comm.linear_q8_allreduce(q, m.weight, self._bias_everywhere(x2.device),
+                                                  float(m.dequant_scale.item()), row_scale=row_scale)
+            else:
+                y = self.comm.linear_q8_allreduce(q, m.weight, m.bias if m.use_bias else None,
+                                                  float(m.dequant_scale.item()), row_scale=row_scale, partials="native")
             return y.view(*x.shape[:-1], m.out_features)
 
         if self.reduce == "int32":
@@ -257,7 +262,7 @@ def _shard_fused_columns(fused, rank: int, world: int, device):
 
 def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: Optional[Dict[str, str]] = None,
                      group=None, dtype=torch.bfloat16, seed: int = 0, glue: bool = True, fused_allreduce: bool = False,
-                     max_tokens: int = 2048):
+                     max_tokens: int = 2048, partials: str = "int32"):
     """The benchmark stack of ``harness.QuantDecoder`` tensor-parallel over `world` ranks: fused q|k|v and
     gate|up column-sharded by head / by intermediate channel, o_proj and down_proj row-sharded with ONE
     all-reduce each (NCCL over NVLink), attention over the local heads, residual stream and norms replicated.
@@ -285,9 +290,10 @@ def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: O
         for name in ("o_proj", "down_proj"):
             full = getattr(layer, name)
             setattr(layer, name, RowParallelLinear(shard_row(full, rank, world).to(device), group=group,
-                                                   has_bias=full.use_bias, reduce="fused" if comm is not None else "native",
+                                                   has_bias=full.use_bias,
+                                                   reduce=("fused" if partials == "int32" else "fused-native") if comm is not None else "native",
                                                    comm=comm))
-        layer.tp_world, layer.tp_group, layer.peer_comm = world, group, comm
+        layer.tp_world, layer.tp_group, layer.peer_comm, layer.peer_partials = world, group, comm, partials
         torch.cuda.empty_cache()
     model.tp_world = world
     return model

@@ -55,9 +55,10 @@ def parse_args():
     ap.add_argument("--parallel", default="dp", choices=["dp", "tp"])
     ap.add_argument("--quant", default="",
                     help="quant_config overrides, e.g. 'out=per-token,fc2=per-token' (BASELINE config 3); default: all per-tensor")
-    ap.add_argument("--tp-reduce", default="auto", choices=["auto", "fused", "nccl"],
+    ap.add_argument("--tp-reduce", default="auto", choices=["auto", "fused", "fused-int32", "nccl"],
                     help="--parallel tp: row-parallel GEMM fused with its all-reduce over peer memory (one launch), "
-                         "or GEMM launch + NCCL all-reduce; auto = fused at 2 GPUs (measured faster), NCCL (NVLS) beyond")
+                         "(16-bit partials = NCCL-native numerics; fused-int32 = exact integer partials), or GEMM launch + NCCL "
+                         "all-reduce; auto = fused at 2 GPUs (measured faster), NCCL (NVLS) beyond")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-glue", action="store_true",
@@ -274,7 +275,8 @@ def run_ours(args, cfg, layers):
         from autosmoothquant_b200.tp import build_tp_decoder
 
         model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank, glue=not args.no_glue,
-                                 fused_allreduce=args.tp_reduce == "fused", max_tokens=args.batch * world * args.seq)
+                                 fused_allreduce=args.tp_reduce.startswith("fused"), max_tokens=args.batch * world * args.seq,
+                                 partials="int32" if args.tp_reduce == "fused-int32" else "native")
         batch = args.batch * world  # weak scaling: the global batch grows with the GPU count
     else:
         model = QuantDecoder(cfg, quant_overrides(args), device=dev, dtype=torch.bfloat16, seed=0, layers=layers,

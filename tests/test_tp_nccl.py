@@ -73,6 +73,12 @@ def _worker(rank, world, port, ret):
         out2 = model(ids, last_token_only=False)
         results["decoder fused all-reduce repeatable"] = bool(torch.equal(out, out2))
         model.peer_comm.close()
+        model = tp.build_tp_decoder(harness.TINY, layers=None, device=dev, world=world, rank=rank, seed=3, glue=True,
+                                    fused_allreduce=True, max_tokens=128, partials="native")
+        ref_nccl = tp.build_tp_decoder(harness.TINY, layers=None, device=dev, world=world, rank=rank, seed=3, glue=True)(ids, last_token_only=False)
+        # 16-bit partials reproduce GEMM + bf16 NCCL all-reduce exactly at world 2 -> the whole stack is bit-identical
+        results["decoder fused-native == decoder NCCL"] = bool(torch.equal(model(ids, last_token_only=False), ref_nccl))
+        model.peer_comm.close()
         ret[rank] = results
     finally:
         dist.destroy_process_group()
