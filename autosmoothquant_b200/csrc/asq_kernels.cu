@@ -777,24 +777,42 @@ struct Seg {
 };
 enum : int { SEG_COMPLETE = 0, SEG_CONTRIB = 1, SEG_OWNER = 2, SEG_AR_CONTRIB = 3, SEG_AR_OWNER = 4 };
 
+// Feature bits of a kernel instantiation.  The full kernel (every epilogue, stream-K, grouping, the fused
+// prologue, ...) is > 1 MB of SASS and every feature added a fixed ~0.3-0.5 us per launch; the launches of the
+// Llama layer therefore use lean instantiations that compile only what they execute, everything else runs the
+// full one.  A launch may use an instantiation iff its needs are a subset of the instantiation's bits.
+enum Feat : int {
+  F_AR = 1,        // fused all-reduce roles (+ the peers' output maps as launch parameters)
+  F_SK = 2,        // stream-K tail
+  F_GROUP = 4,     // grouped / batched weight selection, skipped padding tiles
+  F_SWIGLU = 8,    // SwiGLU epilogue
+  F_ROPE = 16,     // RoPE epilogue
+  F_DEQ16 = 32,    // the standard staged 16-bit dequant epilogue
+  F_OUT_ANY = 64,  // 4-byte staged outputs, raw int32, alpha/beta, direct (unstaged) stores
+  F_PHASE1 = 128,  // fused activation-quantisation prologue
+  F_FULL = F_SK | F_GROUP | F_SWIGLU | F_ROPE | F_DEQ16 | F_OUT_ANY | F_PHASE1,
+};
+
+template <int FEAT>
 struct TileWalk {
   const LinearParams& p;
   int worker, W, round, g, g_end;
   __device__ static long long sk_begin(const LinearParams& p, int w) {
     return static_cast<long long>(w) * p.sk_total / p.sk_workers;
   }
+  __device__ bool sk_on() const { return (FEAT & F_SK) != 0 && p.sk_enabled != 0; }
   __device__ TileWalk(const LinearParams& p_, int worker_, int W_) : p(p_), worker(worker_), W(W_), round(0), g(0), g_end(0) {
-    if (p_.sk_enabled && worker_ < p_.sk_workers) {
+    if (sk_on() && worker_ < p_.sk_workers) {
       g = static_cast<int>(sk_begin(p_, worker_));
       g_end = static_cast<int>(sk_begin(p_, worker_ + 1));
-    } else if (!p_.sk_enabled && worker_ < p_.tail_tiles) {
+    } else if (!sk_on() && worker_ < p_.tail_tiles) {
       g = worker_;  // plain tail: one left-over tile per worker
       g_end = worker_ + 1;
     }
   }
   __device__ void set_tile(Seg& sg, int t) const {
     int n_blk;
-    if (p.ar_world > 1) {
+    if ((FEAT & F_AR) != 0 && p.ar_world > 1) {
       // walk order of this rank: the tiles owned by rank+1, rank+2, ... first, its own tiles last
       int i = t, owner = p.ar_rank;
       for (int s = 1; s <= p.ar_world; ++s) {
@@ -808,8 +826,10 @@ struct TileWalk {
       sg.role = (owner == p.ar_rank) ? SEG_AR_OWNER : SEG_AR_CONTRIB;
     }
     tile_coords(t, p, sg.m_blk, n_blk);
-    sg.group = (p.group_of_blk != nullptr) ? __ldg(p.group_of_blk + sg.m_blk * p.tile_m_blocks)
-               : (p.batch_rows > 0 ? (sg.m_blk * p.tile_m_blocks * BLOCK_M) / p.batch_rows : 0);
+    sg.group = 0;
+    if ((FEAT & F_GROUP) != 0)
+      sg.group = (p.group_of_blk != nullptr) ? __ldg(p.group_of_blk + sg.m_blk * p.tile_m_blocks)
+                 : (p.batch_rows > 0 ? (sg.m_blk * p.tile_m_blocks * BLOCK_M) / p.batch_rows : 0);
     const int U = p.tile_units;  // tile width in 64-column units: 4, or fewer for decode-sized problems
     sg.col0 = n_blk * U * UNIT_N;
     sg.width = min(U, p.n_units - n_blk * U) * UNIT_N;
@@ -825,7 +845,7 @@ struct TileWalk {
       if (sg.group >= 0) return true;  // group -1: padding rows of a grouped launch, nothing to compute
     }
     if (g >= g_end) return false;
-    if (!p.sk_enabled) {
+    if (!sk_on()) {
       while (g < g_end) {
         set_tile(sg, p.rounds * W + g);
         ++g;
@@ -878,8 +898,15 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
-struct PeerMaps {
-  CUtensorMap m[7];  // output maps of the other ranks' y buffers (all-reduce mode), in rank order skipping self
+// Output maps of the other ranks' y buffers (all-reduce mode), in rank order skipping self.  Only the AR
+// instantiations of the kernel carry them: 896 bytes of launch parameters cost ~2 us per launch (measured).
+template <bool AR>
+struct PeerMapsT {
+  char unused;
+};
+template <>
+struct PeerMapsT<true> {
+  CUtensorMap m[7];
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -887,11 +914,15 @@ struct PeerMaps {
 // super tile: pair p computes columns [p*256, p*256+256), both pairs need the same activation rows, so every
 // CTA fetches only HALF of its 128 A rows and multicasts them to its twin in the other pair.  Per k-block a
 // CTA then pulls 8 KB (A) + 16 KB (W) from L2 instead of 32 KB; the main loop is L2-feed bound.
-template <bool FP8, int CG, int MC>
+template <bool FP8, int CG, int MC, int FEAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmBu, const __grid_constant__ CUtensorMap tmY,
-                  const __grid_constant__ PeerMaps tmPeers, const LinearParams p) {
+                  const __grid_constant__ PeerMapsT<(FEAT & F_AR) != 0> tmPeers, const LinearParams p) {
+  constexpr bool AR = (FEAT & F_AR) != 0;
+  constexpr bool kSK = (FEAT & F_SK) != 0, kGROUP = (FEAT & F_GROUP) != 0, kSWIGLU = (FEAT & F_SWIGLU) != 0;
+  constexpr bool kROPE = (FEAT & F_ROPE) != 0, kDEQ16 = (FEAT & F_DEQ16) != 0, kOUT_ANY = (FEAT & F_OUT_ANY) != 0;
+  constexpr bool kLoop = (FEAT & (F_DEQ16 | F_OUT_ANY | F_SK | F_AR)) != 0;  // the generic per-group epilogue loop
   using Cfg = TileCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -916,7 +947,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int pair_idx = static_cast<int>(cluster_rank) / CG;       // which pair of the cluster (MC == 2)
   const int num_workers = gridDim.x / (CG * MC);                  // CTAs, CTA pairs or 4-CTA clusters
   const int worker = blockIdx.x / (CG * MC);
-  const bool fused = (p.x != nullptr);
+  const bool fused = (FEAT & F_PHASE1) != 0 && (p.x != nullptr);
   if (threadIdx.x == 0) ASQ_STAMP(0);
 
   if (warp == 0 && lane == 0) {
@@ -954,7 +985,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
-      TileWalk walk(p, worker, num_workers);
+      TileWalk<FEAT> walk(p, worker, num_workers);
       Seg sg;
       while (walk.next(sg)) {
         const int m_blk = sg.m_blk;
@@ -1015,7 +1046,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      TileWalk walk(p, worker, num_workers);
+      TileWalk<FEAT> walk(p, worker, num_workers);
       Seg sg;
       for (; walk.next(sg); ++it) {
         int width = sg.width;
@@ -1067,7 +1098,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool tensor_dyn = (p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC);
       const float ts = tensor_dyn ? tensor_scale_phase(p, ew * gridDim.x + blockIdx.x, warps_total, warps_total, lane) : 0.f;
       for (int row = ew * gridDim.x + blockIdx.x; row < p.M; row += warps_total) {
-        if (p.group_of_blk != nullptr && __ldg(p.group_of_blk + row / BLOCK_M) < 0) continue;  // padding block of a grouped launch
+        if (kGROUP && p.group_of_blk != nullptr && __ldg(p.group_of_blk + row / BLOCK_M) < 0) continue;  // padding block of a grouped launch
         const float s = quantize_row_any<FP8>(p, row, lane, ts);
         if (lane == 0 && (p.act_mode == ASQ_ACT_PER_TOKEN || p.act_mode == ASQ_ACT_ROW_SCALE_GIVEN || tensor_dyn)) {
           p.row_scale[row] = s;
@@ -1094,9 +1125,9 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                (p.epi_kind == EPI_DEQUANT || p.epi_kind == EPI_SWIGLU);
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     // all-reduce mode: this launch's epoch = 1 + the epoch of the last launch that finished on this rank
-    const uint32_t ar_epoch = (p.ar_world > 1) ? __ldcg(p.ar_ctl[p.ar_rank]) + 1u : 0u;
+    const uint32_t ar_epoch = (AR && p.ar_world > 1) ? __ldcg(p.ar_ctl[p.ar_rank]) + 1u : 0u;
     int it = 0;
-    TileWalk walk(p, worker, num_workers);
+    TileWalk<FEAT> walk(p, worker, num_workers);
     Seg sg;
     for (; walk.next(sg); ++it) {
       const int m_blk = sg.m_blk;
@@ -1110,13 +1141,13 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
       const int ngroups = width / UNIT_N;
       float rs = 0.f;
-      const float tile_scale = (p.group_scale != nullptr) ? __ldg(p.group_scale + sg.group) : p.dequant_scale;
-      const float tile_scale_up = (p.group_scale_up != nullptr) ? __ldg(p.group_scale_up + sg.group) : p.dequant_scale_up;
+      const float tile_scale = (kGROUP && p.group_scale != nullptr) ? __ldg(p.group_scale + sg.group) : p.dequant_scale;
+      const float tile_scale_up = (kGROUP && p.group_scale_up != nullptr) ? __ldg(p.group_scale_up + sg.group) : p.dequant_scale_up;
       // stream-K owner: the workers after this one hold the rest of this tile's K range
       int n_contrib = 0;
-      if (sg.role == SEG_OWNER) {
+      if (kSK && sg.role == SEG_OWNER) {
         const long long tile_end = static_cast<long long>(sg.tile_g0) + p.num_k_blocks;
-        for (int c = worker + 1; c < p.sk_workers && TileWalk::sk_begin(p, c) < tile_end; ++c) ++n_contrib;
+        for (int c = worker + 1; c < p.sk_workers && TileWalk<FEAT>::sk_begin(p, c) < tile_end; ++c) ++n_contrib;
         if (lane == 0) {
           for (int c = 0; c < n_contrib; ++c) {
             const uint32_t* f = sk_flag(p, worker + 1 + c, CG, cta_rank, ew);
@@ -1125,7 +1156,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         __syncwarp();
       }
-      if (sg.role == SEG_AR_OWNER) {  // the other ranks' partials of this tile must have landed in our buffer
+      if (AR && sg.role == SEG_AR_OWNER) {  // the other ranks' partials of this tile must have landed in our buffer
         if (lane == 0) {
           for (int sl = 0; sl < p.ar_world - 1; ++sl) {
             const uint32_t* f = p.ar_ctl[p.ar_rank] + AR_FLAG_BASE + ar_index(p, sl, sg.ar_tile / p.ar_world, CG, cta_rank, ew);
@@ -1138,7 +1169,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       if (it == 0 && ew == 0 && lane == 0) ASQ_STAMP(5);
       if (per_token_epi && row < p.M) rs = __ldcg(p.row_scale + row);
-      if (p.epi_kind == EPI_SWIGLU) {
+      if (kSWIGLU && p.epi_kind == EPI_SWIGLU) {
         // Interleaved gate|up tile: group g = 32 gate columns + the 32 matching up columns -> 32 outputs.  This
         // warp takes groups 2*half and 2*half+1, i.e. 64 adjacent output columns of its 32 rows: one staging
         // tile (int8: 32 rows x 64 B, dense; 16-bit: 32 rows x 128 B, swizzled) and one TMA store per tile.
@@ -1185,7 +1216,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      if (p.rope_cos != nullptr) {
+      if (kROPE && p.rope_cos != nullptr) {
         // Fused q|k|v projection with RoPE: this warp takes groups 2*half and 2*half+1 = one whole 128-wide
         // head of its 32 rows, so both operands of the rotation (columns d and d + 64) are in its registers.
         // Both staging buffers are used per tile (one per 64-column group), then two TMA stores.
@@ -1237,13 +1268,13 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       int chunk_pair = 0;  // index of the (r0, r1) pair inside this warp's stream-K region
 #pragma unroll 1
-      for (int g = half; g < ngroups; g += 2, ++chunk_pair) {
+      for (int g = half; kLoop && g < ngroups; g += 2, ++chunk_pair) {
         const uint32_t taddr = taddr0 + g * UNIT_N;
         const int col0 = tile_col0 + g * UNIT_N;
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(taddr, r0);
         tmem_ld_32x32(taddr + 32, r1);
-        if (sg.role == SEG_CONTRIB) {
+        if (kSK && sg.role == SEG_CONTRIB) {
           // raw partial accumulators -> scratch, coalesced: uint4 index (chunk*8 + quad16)*32 + lane
           tmem_ld_wait();
           uint4* dst = reinterpret_cast<uint4*>(sk_warp_base(p, worker, CG, cta_rank, ew)) + chunk_pair * 2 * 8 * 32 + lane;
@@ -1253,7 +1284,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 8; ++q) __stcg(dst + (8 + q) * 32, make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]));
           continue;
         }
-        if (sg.role == SEG_AR_CONTRIB && p.ar_partial16) {
+        if (AR && sg.role == SEG_AR_CONTRIB && p.ar_partial16) {
           // dequantised partial (+ bias on the rank that holds it), rounded to the output dtype: 2 bytes per element
           tmem_ld_wait();
           const int owner = sg.ar_tile % p.ar_world;
@@ -1272,7 +1303,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 4; ++q) dst[(4 + q) * 32] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
           continue;
         }
-        if (sg.role == SEG_AR_CONTRIB) {
+        if (AR && sg.role == SEG_AR_CONTRIB) {
           // raw partial accumulators -> the owner's receive buffer over NVLink, coalesced 512-byte warp stores
           tmem_ld_wait();
           const int owner = sg.ar_tile % p.ar_world;
@@ -1285,7 +1316,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 8; ++q) dst[(8 + q) * 32] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
           continue;
         }
-        if (sg.role == SEG_AR_OWNER && !p.ar_partial16) {
+        if (AR && sg.role == SEG_AR_OWNER && !p.ar_partial16) {
           tmem_ld_wait();
           for (int sl = 0; sl < p.ar_world - 1; ++sl) {  // fixed source order: deterministic fp32 sums
             const uint4* src = reinterpret_cast<const uint4*>(p.ar_recv[p.ar_rank] + ar_index(p, sl, sg.ar_tile / p.ar_world, CG, cta_rank, ew) * SK_WARP_WORDS) +
@@ -1310,7 +1341,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (sg.role == SEG_OWNER) {
+        if (kSK && sg.role == SEG_OWNER) {
           tmem_ld_wait();
           for (int c = 0; c < n_contrib; ++c) {
             const uint4* src = reinterpret_cast<const uint4*>(sk_warp_base(p, worker + 1 + c, CG, cta_rank, ew)) + chunk_pair * 2 * 8 * 32 + lane;
@@ -1334,7 +1365,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (staged && out16) {
+        if (kDEQ16 && staged && out16) {
           // 64 output columns (two TMEM chunks) fill one 128-byte wide staging tile
           const uint32_t buf = stage_base + (gcount % EPI_NBUF) * EPI_BUF_BYTES;
           if (gcount >= EPI_NBUF) {  // the store that last used this buffer must have read it
@@ -1344,7 +1375,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
           float v[32];
           uint32_t w[16];
-          const bool ar16_owner = (sg.role == SEG_AR_OWNER && p.ar_partial16);
+          const bool ar16_owner = (AR && sg.role == SEG_AR_OWNER && p.ar_partial16);
           const bool bf_out = (p.y_dtype == ASQ_BF16);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1376,7 +1407,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             pack_out16(v, w, bf_out);
             stage_words<16>(buf, lane, h * 4, w);
           }
-          if (p.ar_y_mc != nullptr && sg.role == SEG_AR_OWNER) {
+          if (AR && p.ar_y_mc != nullptr && sg.role == SEG_AR_OWNER) {
             // NVLS: read the staged tile back row-major (8 lanes x 16 bytes = one 128-byte row) and multicast it
             __syncwarp();
 #pragma unroll
@@ -1398,12 +1429,14 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (lane == 0 && row0 < p.M && col0 < p.N) {
               tma_store_2d(&tmY, buf, col0 * elem, row0);
-              for (int pr = 0; pr < p.ar_world - 1; ++pr) tma_store_2d(&tmPeers.m[pr], buf, col0 * elem, row0);  // all-gather by stores
+              if constexpr (AR) {
+                for (int pr = 0; pr < p.ar_world - 1; ++pr) tma_store_2d(&tmPeers.m[pr], buf, col0 * elem, row0);  // all-gather by stores
+              }
               tma_store_commit();
             }
           }
           ++gcount;
-        } else if (staged) {
+        } else if (kOUT_ANY && staged) {
           // 4-byte outputs: each TMEM chunk (32 columns) is one 128-byte wide staging tile
           tmem_ld_wait();
 #pragma unroll
@@ -1433,7 +1466,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             ++gcount;
           }
-        } else {
+        } else if (kOUT_ANY) {
           tmem_ld_wait();
           store_chunk_direct<FP8>(r0, row, col0, rs, p);
           store_chunk_direct<FP8>(r1, row, col0 + 32, rs, p);
@@ -1444,14 +1477,14 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
         else         mbar_arrive(tempty_bar(acc));
-        if (sg.role == SEG_CONTRIB) st_release_gpu(sk_flag(p, worker, CG, cta_rank, ew), 1u);  // partial published
-        if (sg.role == SEG_AR_CONTRIB) {  // __syncwarp above ordered the other lanes' stores before this fence
+        if (kSK && sg.role == SEG_CONTRIB) st_release_gpu(sk_flag(p, worker, CG, cta_rank, ew), 1u);  // partial published
+        if (AR && sg.role == SEG_AR_CONTRIB) {  // __syncwarp above ordered the other lanes' stores before this fence
           const int owner = sg.ar_tile % p.ar_world;
           const int slot = (p.ar_rank - owner - 1 + p.ar_world) % p.ar_world;
           fence_acq_rel_sys();
           st_release_sys(p.ar_ctl[owner] + AR_FLAG_BASE + ar_index(p, slot, sg.ar_tile / p.ar_world, CG, cta_rank, ew), ar_epoch);
         }
-        if (sg.role == SEG_OWNER)
+        if (kSK && sg.role == SEG_OWNER)
           for (int c = 0; c < n_contrib; ++c) *sk_flag(p, worker + 1 + c, CG, cta_rank, ew) = 0u;  // consumed: re-arm
       }
     }
@@ -1466,7 +1499,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (threadIdx.x == 0) ASQ_STAMP(7);
-  if (p.ar_world > 1 && threadIdx.x == 0) {
+  if (AR && p.ar_world > 1 && threadIdx.x == 0) {
     // This CTA's tiles are stored everywhere (each epilogue warp waited for its TMA stores before the sync above).
     // The last CTA of the rank tells every peer "rank r finished launch e", waits for the same word from every
     // peer (their stores into OUR y and their reads of OUR partials are then complete) and advances the epoch.
@@ -1660,16 +1693,17 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 
 // ---------------------------------------------------------------------- kernel launchers
 // The six instantiations of the kernel dominate the build time, so the build compiles this file once per
-// instantiation in parallel (-DASQ_TU=1..6: only the kernel + its launcher) plus once for the host side
+// instantiation in parallel (-DASQ_TU=1..12: only the kernel + its launcher) plus once for the host side
 // (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
 namespace asq_launch {
 constexpr int kMaxDevices = 64;
 
-template <bool FP8, int CG, int MC>
+template <bool FP8, int CG, int MC, int FEAT>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBu, const CUtensorMap& tmY,
-               const asq::PeerMaps& tmPeers, const asq::LinearParams& p, int workers, cudaStream_t stream) {
+               const asq::PeerMapsT<(FEAT & asq::F_AR) != 0>& tmPeers, const asq::LinearParams& p, int workers,
+               cudaStream_t stream) {
   using Cfg = asq::TileCfg<CG>;
-  auto kern = asq::asq_linear_kernel<FP8, CG, MC>;
+  auto kern = asq::asq_linear_kernel<FP8, CG, MC, FEAT>;
   cudaError_t e;
   {
     static bool attr_set[kMaxDevices] = {};  // per template instantiation, per device
@@ -1709,7 +1743,7 @@ int max_multicast_clusters(int dev) {
   static bool known[kMaxDevices] = {};
   if (known[dev]) return cached[dev];
   using Cfg = asq::TileCfg<2>;
-  auto kern = asq::asq_linear_kernel<FP8, 2, 2>;
+  auto kern = asq::asq_linear_kernel<FP8, 2, 2, asq::F_FULL>;
   int n = 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) == cudaSuccess) {
     cudaLaunchConfig_t cfg;
@@ -1739,29 +1773,53 @@ int max_multicast_clusters(int dev) {
 #else
 #define ASQ_LAUNCH_DECL template
 #endif
-#define ASQ_LAUNCH_INST(FP8, CG, MC)                                                                            \
-  ASQ_LAUNCH_DECL int launch_cfg<FP8, CG, MC>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,        \
-                                              const CUtensorMap&, const asq::PeerMaps&, const asq::LinearParams&, \
-                                              int, cudaStream_t);
+#define ASQ_LAUNCH_INST(FP8, CG, MC, FEAT)                                                                      \
+  ASQ_LAUNCH_DECL int launch_cfg<FP8, CG, MC, FEAT>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,  \
+                                                    const CUtensorMap&,                                          \
+                                                    const asq::PeerMapsT<((FEAT) & asq::F_AR) != 0>&,             \
+                                                    const asq::LinearParams&, int, cudaStream_t);
+// lean instantiations for the launches of a Llama layer (int8, CTA pairs): see asq::Feat
+#define ASQ_LEAN_PLAIN (asq::F_DEQ16)
+#define ASQ_LEAN_PHASE1 (asq::F_DEQ16 | asq::F_PHASE1)
+#define ASQ_LEAN_SWIGLU (asq::F_SWIGLU)
+#define ASQ_LEAN_ROPE (asq::F_ROPE)
 #if ASQ_TU == 0 || ASQ_TU == 1
-ASQ_LAUNCH_INST(false, 1, 1)
+ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 2
-ASQ_LAUNCH_INST(false, 2, 1)
+ASQ_LAUNCH_INST(false, 2, 1, asq::F_FULL)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 3
-ASQ_LAUNCH_INST(true, 1, 1)
+ASQ_LAUNCH_INST(true, 1, 1, asq::F_FULL)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 4
-ASQ_LAUNCH_INST(true, 2, 1)
+ASQ_LAUNCH_INST(true, 2, 1, asq::F_FULL)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 5
-ASQ_LAUNCH_INST(false, 2, 2)
+ASQ_LAUNCH_INST(false, 2, 2, asq::F_FULL)
 ASQ_LAUNCH_DECL int max_multicast_clusters<false>(int);
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 6
-ASQ_LAUNCH_INST(true, 2, 2)
+ASQ_LAUNCH_INST(true, 2, 2, asq::F_FULL)
 ASQ_LAUNCH_DECL int max_multicast_clusters<true>(int);
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 7
+ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL | asq::F_AR)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 8
+ASQ_LAUNCH_INST(false, 2, 1, asq::F_FULL | asq::F_AR)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 9
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PLAIN)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 10
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 11
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_SWIGLU)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 12
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_ROPE)
 #endif
 #endif  // ASQ_TU
 }  // namespace asq_launch
@@ -1938,10 +1996,11 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       tmY = tmA;  // unused, but must be a valid descriptor
     }
   }
-  asq::PeerMaps tmPeers;
-  memset(&tmPeers, 0, sizeof(tmPeers));
   if (p.ar_world > 1) {
     if (!p.tma_store || peer_y == nullptr) return fail(ASQ_ERR_INVALID, "all-reduce mode needs a 16-byte aligned 16-bit output row pitch");
+    if (fp8 || mc != 1) return fail(ASQ_ERR_UNSUPPORTED, "all-reduce mode exists for the int8 path only");
+    asq::PeerMapsT<true> tmPeers;
+    memset(&tmPeers, 0, sizeof(tmPeers));
     const long long row_bytes = static_cast<long long>(p.N) * 2;
     for (int i = 0; i < p.ar_world - 1; ++i) {
       rc = make_tmap(&tmPeers.m[i], peer_y[i], p.M, row_bytes, 32);
@@ -1949,13 +2008,38 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     }
     p.ar_tiles = p.num_m_blocks * p.num_n_blocks;
     p.ar_cnt_max = (p.ar_tiles + p.ar_world - 1) / p.ar_world;
+    return cg == 2 ? launch_cfg<false, 2, 1, asq::F_FULL | asq::F_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
+                   : launch_cfg<false, 1, 1, asq::F_FULL | asq::F_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
   }
-  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
-                          : launch_cfg<false, 2, 2>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
-  if (fp8) return cg == 2 ? launch_cfg<true, 2, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
-                          : launch_cfg<true, 1, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
-  return cg == 2 ? launch_cfg<false, 2, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
-                 : launch_cfg<false, 1, 1>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
+  const asq::PeerMapsT<false> none{};
+  constexpr int FULL = asq::F_FULL;
+  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
+                          : launch_cfg<false, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  if (fp8) return cg == 2 ? launch_cfg<true, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
+                          : launch_cfg<true, 1, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  if (cg == 2) {
+    // What this launch needs; a lean instantiation is used when it covers exactly that (ASQ_LEAN=0 disables).
+    static int lean_env = -1;
+    if (lean_env < 0) { const char* e = getenv("ASQ_LEAN"); lean_env = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
+    int need = 0;
+    if (p.x != nullptr) need |= asq::F_PHASE1;
+    if (p.sk_enabled) need |= asq::F_SK;
+    if (p.group_of_blk != nullptr || p.batch_rows > 0) need |= asq::F_GROUP;
+    if (p.epi_kind == asq::EPI_SWIGLU) need |= asq::F_SWIGLU;
+    else if (p.rope_cos != nullptr) need |= asq::F_ROPE;
+    else if (p.epi_kind == asq::EPI_DEQUANT && p.tma_store && out16 && p.out_fq_scale == 0.f) need |= asq::F_DEQ16;
+    else need |= asq::F_OUT_ANY;
+    if (p.dbg != nullptr) need |= asq::F_OUT_ANY;  // timeline runs: always the full kernel
+    if (lean_env) {
+      if (need == (ASQ_LEAN_PLAIN)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_SWIGLU)) return launch_cfg<false, 2, 1, ASQ_LEAN_SWIGLU>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_ROPE)) return launch_cfg<false, 2, 1, ASQ_LEAN_ROPE>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    }
+    return launch_cfg<false, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  }
+  return launch_cfg<false, 1, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
 }
 
 int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {

@@ -126,8 +126,13 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // the stream is still draining: pdl_launch_dependents() lets the successor's CTAs be scheduled as SMs free up,
 // pdl_wait() blocks until the predecessor grid has completed and its memory is visible.  Everything that
 // touches global memory comes after pdl_wait(); without the launch attribute both are no-ops.
+#ifdef ASQ_NO_PDL
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
