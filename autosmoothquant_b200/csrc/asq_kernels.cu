@@ -1693,7 +1693,7 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 
 // ---------------------------------------------------------------------- kernel launchers
 // The six instantiations of the kernel dominate the build time, so the build compiles this file once per
-// instantiation in parallel (-DASQ_TU=1..12: only the kernel + its launcher) plus once for the host side
+// instantiation in parallel (-DASQ_TU=1..14: only the kernel + its launcher) plus once for the host side
 // (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
 namespace asq_launch {
 constexpr int kMaxDevices = 64;
@@ -1783,6 +1783,7 @@ int max_multicast_clusters(int dev) {
 #define ASQ_LEAN_PHASE1 (asq::F_DEQ16 | asq::F_PHASE1)
 #define ASQ_LEAN_SWIGLU (asq::F_SWIGLU)
 #define ASQ_LEAN_ROPE (asq::F_ROPE)
+#define ASQ_LEAN_AR (asq::F_AR | asq::F_DEQ16)
 #if ASQ_TU == 0 || ASQ_TU == 1
 ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL)
 #endif
@@ -1820,6 +1821,12 @@ ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_SWIGLU)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 12
 ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_ROPE)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 13
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_AR)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 14
+ASQ_LAUNCH_INST(true, 2, 1, ASQ_LEAN_PHASE1)
 #endif
 #endif  // ASQ_TU
 }  // namespace asq_launch
@@ -2008,6 +2015,10 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     }
     p.ar_tiles = p.num_m_blocks * p.num_n_blocks;
     p.ar_cnt_max = (p.ar_tiles + p.ar_world - 1) / p.ar_world;
+    const char* lean = getenv("ASQ_LEAN");
+    if (cg == 2 && p.x == nullptr && !p.sk_enabled && p.epi_kind == asq::EPI_DEQUANT && p.out_fq_scale == 0.f && p.dbg == nullptr &&
+        !(lean != nullptr && lean[0] == '0'))
+      return launch_cfg<false, 2, 1, ASQ_LEAN_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
     return cg == 2 ? launch_cfg<false, 2, 1, asq::F_FULL | asq::F_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
                    : launch_cfg<false, 1, 1, asq::F_FULL | asq::F_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
   }
@@ -2015,8 +2026,17 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   constexpr int FULL = asq::F_FULL;
   if (mc == 2) return fp8 ? launch_cfg<true, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
                           : launch_cfg<false, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
-  if (fp8) return cg == 2 ? launch_cfg<true, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
-                          : launch_cfg<true, 1, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  if (fp8) {
+    const char* lean = getenv("ASQ_LEAN");
+    const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
+    // the FP8 per-token / static module forward (BASELINE config 5): fused prologue + 16-bit dequant epilogue
+    if (cg == 2 && p.x != nullptr && !p.sk_enabled && p.group_of_blk == nullptr && p.batch_rows == 0 && p.rope_cos == nullptr &&
+        p.epi_kind == asq::EPI_DEQUANT && p.tma_store && out16 && p.out_fq_scale == 0.f && p.dbg == nullptr &&
+        p.act_mode != ASQ_ACT_PER_TENSOR_DYNAMIC && !(lean != nullptr && lean[0] == '0'))
+      return launch_cfg<true, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    return cg == 2 ? launch_cfg<true, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
+                   : launch_cfg<true, 1, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  }
   if (cg == 2) {
     // What this launch needs; a lean instantiation is used when it covers exactly that (ASQ_LEAN=0 disables).
     static int lean_env = -1;
