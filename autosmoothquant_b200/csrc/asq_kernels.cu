@@ -1693,7 +1693,7 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 
 // ---------------------------------------------------------------------- kernel launchers
 // The six instantiations of the kernel dominate the build time, so the build compiles this file once per
-// instantiation in parallel (-DASQ_TU=1..14: only the kernel + its launcher) plus once for the host side
+// instantiation in parallel (-DASQ_TU=1..16: only the kernel + its launcher) plus once for the host side
 // (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
 namespace asq_launch {
 constexpr int kMaxDevices = 64;
@@ -1784,6 +1784,8 @@ int max_multicast_clusters(int dev) {
 #define ASQ_LEAN_SWIGLU (asq::F_SWIGLU)
 #define ASQ_LEAN_ROPE (asq::F_ROPE)
 #define ASQ_LEAN_AR (asq::F_AR | asq::F_DEQ16)
+#define ASQ_LEAN_PLAIN_SK (asq::F_DEQ16 | asq::F_SK)
+#define ASQ_LEAN_PHASE1_SK (asq::F_DEQ16 | asq::F_PHASE1 | asq::F_SK)
 #if ASQ_TU == 0 || ASQ_TU == 1
 ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL)
 #endif
@@ -1827,6 +1829,12 @@ ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_AR)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 14
 ASQ_LAUNCH_INST(true, 2, 1, ASQ_LEAN_PHASE1)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 15
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PLAIN_SK)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 16
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_SK)
 #endif
 #endif  // ASQ_TU
 }  // namespace asq_launch
@@ -2056,6 +2064,8 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_SWIGLU)) return launch_cfg<false, 2, 1, ASQ_LEAN_SWIGLU>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_ROPE)) return launch_cfg<false, 2, 1, ASQ_LEAN_ROPE>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PLAIN_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PHASE1_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
     }
     return launch_cfg<false, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
   }
