@@ -46,6 +46,8 @@ EXPORTED_SYMBOLS = (
     "asq_w8a8_linear_q8",
     "asq_w8a8_gateup_swiglu_q8",
     "asq_w8a8_linear_q8_rope",
+    "asq_w8a8_linear_res",
+    "asq_w8a8_linear_q8_res",
     "asq_w8a8_grouped_linear",
     "asq_i8bmm",
     "asq_ar_buffer_bytes",
@@ -127,6 +129,11 @@ def load():
         lib.asq_w8a8_gateup_swiglu_q8.restype = c_i
         lib.asq_w8a8_gateup_swiglu_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i64, c_i64, c_i64, c_f, c_f,
                                                   c_vp, c_f, c_i, c_vp]
+        lib.asq_w8a8_linear_res.restype = c_i
+        lib.asq_w8a8_linear_res.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f,
+                                            c_vp, c_vp, c_i, c_vp, c_sz, c_vp]
+        lib.asq_w8a8_linear_q8_res.restype = c_i
+        lib.asq_w8a8_linear_q8_res.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp, c_vp]
         lib.asq_w8a8_linear_q8_rope.restype = c_i
         lib.asq_w8a8_linear_q8_rope.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
                                                 c_vp, c_vp, c_i64, c_i64, c_i64, c_i, c_vp]
@@ -238,10 +245,12 @@ def w8a8_linear(
     out_dtype: Optional[torch.dtype] = None,
     row_scale_out: Optional[torch.Tensor] = None,
     div_mode: Optional[int] = None,
+    residual: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Fused quantise -> INT8 GEMM -> dequant (+bias) for a 2-D ``x`` [M,K]; returns [M,N]."""
+    """Fused quantise -> INT8 GEMM -> dequant (+bias) for a 2-D ``x`` [M,K]; returns [M,N].
+    residual [M,N] (16-bit, the output dtype): returns T(residual + T(linear output)) from the same launch."""
     global _launches
-    dev = _require_cuda(x, weight, bias, col_scale, row_scale_out)
+    dev = _require_cuda(x, weight, bias, col_scale, row_scale_out, residual)
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
         raise ValueError(f"shape mismatch: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
     if weight.dtype != torch.int8:
@@ -264,11 +273,20 @@ def w8a8_linear(
         stream = _stream(dev)
         need = lib.asq_workspace_bytes(M, K)
         ws, ws_bytes = _workspace(dev, stream, need)
-        rc = lib.asq_w8a8_linear(
-            x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
-            M, N, K, act_mode, float(quant_scale), float(dequant_scale), _ptr(col_scale), _ptr(row_scale_out),
-            _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
-        )
+        if residual is not None:
+            if residual.shape != (M, N) or residual.dtype != out_dtype or not residual.is_contiguous():
+                raise ValueError("residual must be a contiguous [M,N] tensor of the output dtype")
+            rc = lib.asq_w8a8_linear_res(
+                x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), residual.data_ptr(), y.data_ptr(), _code(out_dtype),
+                M, N, K, act_mode, float(quant_scale), float(dequant_scale), _ptr(col_scale), _ptr(row_scale_out),
+                _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
+            )
+        else:
+            rc = lib.asq_w8a8_linear(
+                x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
+                M, N, K, act_mode, float(quant_scale), float(dequant_scale), _ptr(col_scale), _ptr(row_scale_out),
+                _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
+            )
     _check(rc)
     _launches += 1
     return y
@@ -423,6 +441,7 @@ def w8a8_linear_q8(
     row_scale: Optional[torch.Tensor] = None,
     out_dtype: torch.dtype = torch.bfloat16,
     rope: Optional[tuple] = None,
+    residual: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """INT8 GEMM + dequant epilogue for activations a fused producer already quantised (no prologue).
     rope = (cos, sin, S, rope_cols): rotate-half RoPE on columns < rope_cols in the epilogue; cos / sin are the
@@ -440,6 +459,17 @@ def w8a8_linear_q8(
     if M == 0:
         return y
     lib = load()
+    if residual is not None:
+        _require_cuda(residual)
+        if rope is not None or residual.shape != (M, N) or residual.dtype != out_dtype or not residual.is_contiguous():
+            raise ValueError("residual must be a contiguous [M,N] tensor of the output dtype (not combinable with rope)")
+        with torch.cuda.device(dev):
+            rc = lib.asq_w8a8_linear_q8_res(xq.data_ptr(), _ptr(row_scale), weight.data_ptr(), _ptr(bias), residual.data_ptr(),
+                                            y.data_ptr(), _code(out_dtype), M, N, K, float(dequant_scale), _ptr(col_scale),
+                                            _stream(dev))
+        _check(rc)
+        _launches += 1
+        return y
     if rope is not None:
         cos, sin, S, rope_cols = rope[:4]
         halves_equal = bool(rope[4]) if len(rope) > 4 else False

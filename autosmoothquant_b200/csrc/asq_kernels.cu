@@ -76,6 +76,10 @@ struct LinearParams {
   // EPI_SWIGLU: w rows interleave 32 gate rows with the 32 matching up rows; the epilogue emits
   // a = T(T(silu(gate)) * up) as T (y_dtype 16-bit) or sat(rint(T(a / out_quant_scale))) as int8, [M, N/2]
   float out_quant_scale, inv_out_quant_scale;
+  // y = T(residual + T(linear output)): the residual-stream add of the decoder block (HF LlamaDecoderLayer:
+  // hidden = residual + o_proj(...) / + down_proj(...)) in the epilogue, so the following norm kernel reads one
+  // tensor instead of two and writes no copy of the stream.  [M, N] of y's 16-bit dtype, may alias y.
+  const void* residual;
   // RoPE in the epilogue (fused q|k|v projection): columns < rope_cols are rotated per 128-wide head with the
   // HF rotate-half formula, position = row % rope_S, tables [rope_S, 128] of the output dtype
   const void* rope_cos;
@@ -790,7 +794,8 @@ enum Feat : int {
   F_DEQ16 = 32,    // the standard staged 16-bit dequant epilogue
   F_OUT_ANY = 64,  // 4-byte staged outputs, raw int32, alpha/beta, direct (unstaged) stores
   F_PHASE1 = 128,  // fused activation-quantisation prologue
-  F_FULL = F_SK | F_GROUP | F_SWIGLU | F_ROPE | F_DEQ16 | F_OUT_ANY | F_PHASE1,
+  F_RESID = 256,   // residual add in the 16-bit epilogue: y = T(residual + T(dequantised result))
+  F_FULL = F_SK | F_GROUP | F_SWIGLU | F_ROPE | F_DEQ16 | F_OUT_ANY | F_PHASE1 | F_RESID,
 };
 
 template <int FEAT>
@@ -923,6 +928,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr bool kSK = (FEAT & F_SK) != 0, kGROUP = (FEAT & F_GROUP) != 0, kSWIGLU = (FEAT & F_SWIGLU) != 0;
   constexpr bool kROPE = (FEAT & F_ROPE) != 0, kDEQ16 = (FEAT & F_DEQ16) != 0, kOUT_ANY = (FEAT & F_OUT_ANY) != 0;
   constexpr bool kLoop = (FEAT & (F_DEQ16 | F_OUT_ANY | F_SK | F_AR)) != 0;  // the generic per-group epilogue loop
+  constexpr bool kRESID = (FEAT & F_RESID) != 0;
   using Cfg = TileCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -1404,6 +1410,26 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
             }
+            if (kRESID && p.residual != nullptr && row < p.M) {
+              // residual add in the activation dtype: T(res + T(v)), the eager `residual + linear(x)`
+              const int c0 = col0 + h * 32;
+              const uint16_t* rrow = reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.N + c0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (c0 + 8 * q < p.N) {  // N % 8 == 0 (host-checked): a 16-byte piece is entirely in or out
+                  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(rrow) + q);
+                  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float lo, hi, x0 = v[8 * q + 2 * i], x1 = v[8 * q + 2 * i + 1];
+                    if (bf_out) { unpack_pair<true>(aw[i], lo, hi); round_pair<true>(x0, x1); }
+                    else        { unpack_pair<false>(aw[i], lo, hi); round_pair<false>(x0, x1); }
+                    v[8 * q + 2 * i] = __fadd_rn(lo, x0);
+                    v[8 * q + 2 * i + 1] = __fadd_rn(hi, x1);
+                  }
+                }
+              }
+            }
             pack_out16(v, w, bf_out);
             stage_words<16>(buf, lane, h * 4, w);
           }
@@ -1693,7 +1719,7 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 
 // ---------------------------------------------------------------------- kernel launchers
 // The six instantiations of the kernel dominate the build time, so the build compiles this file once per
-// instantiation in parallel (-DASQ_TU=1..16: only the kernel + its launcher) plus once for the host side
+// instantiation in parallel (-DASQ_TU=1..18: only the kernel + its launcher) plus once for the host side
 // (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
 namespace asq_launch {
 constexpr int kMaxDevices = 64;
@@ -1786,6 +1812,8 @@ int max_multicast_clusters(int dev) {
 #define ASQ_LEAN_AR (asq::F_AR | asq::F_DEQ16)
 #define ASQ_LEAN_PLAIN_SK (asq::F_DEQ16 | asq::F_SK)
 #define ASQ_LEAN_PHASE1_SK (asq::F_DEQ16 | asq::F_PHASE1 | asq::F_SK)
+#define ASQ_LEAN_PLAIN_RESID (asq::F_DEQ16 | asq::F_RESID)
+#define ASQ_LEAN_PHASE1_RESID (asq::F_DEQ16 | asq::F_PHASE1 | asq::F_RESID)
 #if ASQ_TU == 0 || ASQ_TU == 1
 ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL)
 #endif
@@ -1835,6 +1863,12 @@ ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PLAIN_SK)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 16
 ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_SK)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 17
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PLAIN_RESID)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 18
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_RESID)
 #endif
 #endif  // ASQ_TU
 }  // namespace asq_launch
@@ -1967,7 +2001,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (sk_env == 1 && (p.rounds > 0 || p.num_k_blocks < 64)) sk_env_effective = 0;  // decode-sized M with a long K only
     constexpr int kMinIters = 4;  // k-blocks per stream-K segment, bounds the fix-up overhead
     const long long total_it = static_cast<long long>(p.tail_tiles) * p.num_k_blocks;
-    if (mc == 1 && sk_env_effective && sk_env && p.tail_tiles > 0 && p.tail_tiles < max_workers && total_it / kMinIters >= 2 && total_it < (1ll << 30)) {
+    if (mc == 1 && p.residual == nullptr && sk_env_effective && sk_env && p.tail_tiles > 0 && p.tail_tiles < max_workers && total_it / kMinIters >= 2 && total_it < (1ll << 30)) {
       if (p.sk_partial != nullptr && p.sk_flags != nullptr && max_workers * cg <= kSkMaxCtas) {  // caller gave a workspace
         long long sw = total_it / kMinIters;
         if (sk_env == 1 && sw > 4ll * p.tail_tiles) sw = 4ll * p.tail_tiles;  // the owner adds its contributors serially
@@ -2010,6 +2044,12 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     } else {
       tmY = tmA;  // unused, but must be a valid descriptor
     }
+  }
+  if (p.residual != nullptr) {
+    const bool out16r = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
+    if (!out16r || !p.tma_store || p.epi_kind != asq::EPI_DEQUANT || p.rope_cos != nullptr || p.ar_world > 1 || p.N % 8 != 0 ||
+        (reinterpret_cast<uintptr_t>(p.residual) & 15))
+      return fail(ASQ_ERR_INVALID, "residual add needs a 16-bit dequantised output with N %% 8 == 0 and a 16-byte aligned residual");
   }
   if (p.ar_world > 1) {
     if (!p.tma_store || peer_y == nullptr) return fail(ASQ_ERR_INVALID, "all-reduce mode needs a 16-byte aligned 16-bit output row pitch");
@@ -2058,12 +2098,15 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     else if (p.rope_cos != nullptr) need |= asq::F_ROPE;
     else if (p.epi_kind == asq::EPI_DEQUANT && p.tma_store && out16 && p.out_fq_scale == 0.f) need |= asq::F_DEQ16;
     else need |= asq::F_OUT_ANY;
+    if (p.residual != nullptr) need |= asq::F_RESID;
     if (p.dbg != nullptr) need |= asq::F_OUT_ANY;  // timeline runs: always the full kernel
     if (lean_env) {
       if (need == (ASQ_LEAN_PLAIN)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_SWIGLU)) return launch_cfg<false, 2, 1, ASQ_LEAN_SWIGLU>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_ROPE)) return launch_cfg<false, 2, 1, ASQ_LEAN_ROPE>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PLAIN_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_RESID>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PHASE1_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_RESID>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_PLAIN_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_PHASE1_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
     }
@@ -2089,7 +2132,7 @@ bool is_float_dtype(int d) { return d == ASQ_F32 || d == ASQ_F16 || d == ASQ_BF1
 int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype,
                  int64_t M, int64_t N, int64_t K, int act_mode, float quant_scale, float dequant_scale,
                  const float* col_scale, float* row_scale_out, int div_mode, void* workspace,
-                 size_t workspace_bytes, void* stream, float out_fq_scale = 0.f) {
+                 size_t workspace_bytes, void* stream, float out_fq_scale = 0.f, const void* residual = nullptr) {
   int rc = check_common(x, w, y, M, N, K);
   if (rc != ASQ_OK) return rc;
   if (!is_float_dtype(x_dtype) || !is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "x/y dtype must be f32, f16 or bf16");
@@ -2123,6 +2166,7 @@ int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const floa
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.x_dtype = x_dtype; p.y_dtype = y_dtype; p.act_mode = act_mode; p.div_mode = div_mode;
   p.epi_kind = asq::EPI_DEQUANT;
+  p.residual = residual;
   p.out_fq_scale = out_fq_scale;
   p.inv_out_fq_scale = out_fq_scale != 0.f ? 1.0f / out_fq_scale : 0.f;
   return launch_linear(fp8, ws.a_q, w, p, static_cast<cudaStream_t>(stream));
@@ -2191,9 +2235,33 @@ int asq_w8a8_linear_q8_rope(const int8_t* xq, const float* row_scale, const int8
   return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream));
 }
 
+int asq_w8a8_linear_res(const void* x, int x_dtype, const int8_t* w, const float* bias, const void* residual, void* y,
+                        int y_dtype, int64_t M, int64_t N, int64_t K, int act_mode, float quant_scale, float dequant_scale,
+                        const float* col_scale, float* row_scale_out, int div_mode, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return fused_linear(false, x, x_dtype, w, bias, y, y_dtype, M, N, K, act_mode, quant_scale, dequant_scale,
+                      col_scale, row_scale_out, div_mode, workspace, workspace_bytes, stream, 0.f, residual);
+}
+
+static int linear_q8_impl(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, const void* residual,
+                          void* y, int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+int asq_w8a8_linear_q8_res(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, const void* residual,
+                           void* y, int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                           void* stream) {
+  return linear_q8_impl(xq, row_scale, w, bias, residual, y, y_dtype, M, N, K, dequant_scale, col_scale, nullptr, 0, stream);
+}
+
 int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,
                        int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
                        void* workspace, size_t workspace_bytes, void* stream) {
+  return linear_q8_impl(xq, row_scale, w, bias, nullptr, y, y_dtype, M, N, K, dequant_scale, col_scale, workspace, workspace_bytes, stream);
+}
+
+static int linear_q8_impl(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, const void* residual,
+                          void* y, int y_dtype, int64_t M, int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                          void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(xq, w, y, M, N, K);
   if (rc != ASQ_OK || M == 0) return rc;
   if (!is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "y dtype must be f32, f16 or bf16");
@@ -2203,7 +2271,7 @@ int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w
   if (rc != ASQ_OK) return rc;
   p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
-  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT;
+  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT; p.residual = residual;
   // phase 1 is skipped (p.x == nullptr); the epilogue reads caller-supplied per-token scales if given
   p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
   p.row_scale = const_cast<float*>(row_scale);

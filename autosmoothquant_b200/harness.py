@@ -246,6 +246,10 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
 
     cfg = layer.cfg
     hd = cfg.head_dim
+    # residual add inside the o_proj / down_proj epilogues: bit-identical, but measured neutral-to-slower on B200
+    # (13.03-13.29 vs 12.96-13.19 ms per step: the uncoalesced residual reads in the epilogue cost what the leaner
+    # norm kernel saves), so it is opt-in
+    fuse_res = getattr(layer, "tp_world", 1) == 1 and os.environ.get("ASQ_RESIDUAL_EPILOGUE", "0") == "1"
     x2, _, q8 = _lib.add_rmsnorm_quant(x2, delta, layer.input_layernorm_weight, cfg.rms_eps)
     qkv_mod = layer.qkv_proj
     nq, nk, nv = (n // hd for n in layer.qkv_sizes)
@@ -268,6 +272,16 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
         q8o, _ = _lib.quantize_act(attn2, _lib.ACT_SCALE, float(om.quant_scale.item()))
         o = _lib.w8a8_linear_q8(q8o, om.weight, om.bias if om.use_bias else None, float(om.dequant_scale.item()),
                                 out_dtype=x2.dtype)
+    elif fuse_res:
+        # residual add in o_proj's epilogue: x2 <- T(x2 + o_proj(attn)); the norm kernel then reads one tensor
+        om = layer.o_proj
+        if om.act_quant == "per-token":
+            mode, qs = _lib.ACT_PER_TOKEN, 1.0
+        else:
+            mode, qs = _lib.ACT_SCALE, float(om.quant_scale.item())
+        x2 = _lib.w8a8_linear(attn2, om.weight, om.bias if om.use_bias else None, mode, qs, float(om.dequant_scale.item()),
+                              residual=x2)
+        o = None
     else:
         o = layer.o_proj(attn2)
     x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
@@ -284,6 +298,10 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
             gu = _lib.w8a8_linear_q8(q8, gu_mod.weight, gu_mod.bias if gu_mod.use_bias else None, 1.0,
                                      col_scale=gu_mod._col_scale(x2.device), out_dtype=x2.dtype)
             _, a = _lib.silu_mul_quant(gu, 1.0, want_q=False, want_a=True)
+        if fuse_res:
+            x2 = _lib.w8a8_linear(a, down.weight, down.bias if down.use_bias else None, _lib.ACT_PER_TOKEN, 1.0,
+                                  float(down.dequant_scale.item()), residual=x2)
+            return x2, None
         return x2, layer.down_proj(a)
     if il is not None:
         # SiLU(gate)*up and down_proj's activation quantisation run in the gate|up GEMM epilogue
@@ -304,6 +322,10 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
             d = comm.linear_q8_allreduce(a8, down.weight, layer.down_proj._bias_everywhere(x2.device),
                                          float(down.dequant_scale.item()))
         return x2, d
+    if fuse_res:  # x2 <- T(x2 + down_proj(a)) in the epilogue; nothing is left to add in the next norm kernel
+        x2 = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
+                                 out_dtype=x2.dtype, residual=x2)
+        return x2, None
     d = _lib.w8a8_linear_q8(a8, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
                             out_dtype=x2.dtype)
     if tp_world > 1:  # row-parallel partial sums -> one all-reduce over NVLink
@@ -362,7 +384,7 @@ class QuantDecoder(nn.Module):
                 x2, delta = _layer_forward_glue(layer, x2, delta, B, S, cos, sin)
             if last_token_only:  # only the last position of every sequence feeds the lm_head
                 x2 = x2.view(B, S, -1)[:, -1, :].contiguous()
-                delta = delta.view(B, S, -1)[:, -1, :].contiguous()
+                delta = delta.view(B, S, -1)[:, -1, :].contiguous() if delta is not None else None
             _, h, _ = _lib.add_rmsnorm_quant(x2, delta, self.norm_weight, self.cfg.rms_eps, want_h=True, want_q=False)
             return self.lm_head(h.view(B, -1, self.cfg.hidden)).float()
         for layer in self.layers:

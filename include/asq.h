@@ -148,6 +148,19 @@ int asq_w8a8_linear_q8(const int8_t* xq, const float* row_scale, const int8_t* w
                        float dequant_scale, const float* col_scale,
                        void* workspace /* nullable */, size_t workspace_bytes, void* stream);
 
+/* asq_w8a8_linear / asq_w8a8_linear_q8 with the decoder block's residual add in the epilogue:
+ *   y = T(residual + T(linear output))     residual [M,N] of y's 16-bit dtype (may alias y), y_dtype F16 | BF16
+ * i.e. `hidden = residual + o_proj(...)` / `residual + down_proj(...)` of the HF decoder layers the reference's
+ * model classes inherit (models/llama.py:218) without the separate add (or the add inside the next norm kernel). */
+int asq_w8a8_linear_res(const void* x, int x_dtype, const int8_t* w, const float* bias, const void* residual,
+                        void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                        int act_mode, float quant_scale, float dequant_scale,
+                        const float* col_scale, float* row_scale_out, int div_mode,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int asq_w8a8_linear_q8_res(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias,
+                           const void* residual, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                           float dequant_scale, const float* col_scale, void* stream);
+
 /* asq_w8a8_linear_q8 for the fused q|k|v projection with HF rotate-half RoPE applied in the epilogue (what
  * asq_rope_inplace does as a second pass over the same tensor): columns [0, rope_cols) — the q and k heads —
  * are rotated per head, position = row % S; the remaining columns (v) are plain dequantised outputs.

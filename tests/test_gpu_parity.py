@@ -531,6 +531,46 @@ def test_glue_stack_swiglu_epilogue_is_bit_identical():
     assert torch.equal(a(ids, last_token_only=False), b(ids, last_token_only=False))
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K", [(300, 520, 256), (2048, 4096, 4096), (64, 72, 64)])
+def test_residual_epilogue_equals_linear_then_add(dtype, M, N, K, exact_div):
+    """y = T(residual + T(linear(x))) from one launch == the linear launch followed by the eager add (what the
+    decoder block's `hidden = residual + o_proj(...)` computes), for the fused (bf16 in) and the int8-in entry."""
+    if M == 2048 and dtype == "f16":
+        pytest.skip("full-size case runs once")
+    td = TORCH_DT[dtype]
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(td).to(DEV)
+    w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = (torch.randn(M, N, generator=g) * 3).to(td).to(DEV)
+    for mode, qs in ((L.ACT_SCALE, 0.031), (L.ACT_PER_TOKEN, 1.0)):
+        plain = L.w8a8_linear(x, w, b, mode, qs, 2.1e-4)
+        got = L.w8a8_linear(x, w, b, mode, qs, 2.1e-4, residual=res)
+        assert torch.equal(got, res + plain)
+    xq, _ = L.quantize_act(x, L.ACT_SCALE, 0.031)
+    plain = L.w8a8_linear_q8(xq, w, None, 2.1e-4, out_dtype=td)
+    got = L.w8a8_linear_q8(xq, w, None, 2.1e-4, out_dtype=td, residual=res)
+    assert torch.equal(got, res + plain)
+    inplace = res.clone()  # the residual may alias the output (the decoder updates its stream in place)
+    rc = L.load().asq_w8a8_linear_q8_res(xq.data_ptr(), None, w.data_ptr(), None, inplace.data_ptr(), inplace.data_ptr(), L._code(td),
+                                         M, N, K, 2.1e-4, None, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and torch.equal(inplace, got)
+
+
+def test_glue_stack_residual_epilogue_is_bit_identical(monkeypatch):
+    from autosmoothquant_b200 import harness
+
+    ids = torch.randint(0, harness.TINY.vocab, (2, 96), generator=torch.Generator().manual_seed(4)).to(DEV)
+    for qc in ({}, {"out": "per-token", "fc2": "per-token"}):
+        model = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=5, fuse_projections=True, glue=True)
+        monkeypatch.setenv("ASQ_RESIDUAL_EPILOGUE", "0")
+        want = model(ids, last_token_only=False)
+        monkeypatch.setenv("ASQ_RESIDUAL_EPILOGUE", "1")
+        assert torch.equal(model(ids, last_token_only=False), want)
+        assert torch.equal(model(ids, last_token_only=True), want[:, -1:, :])
+
+
 def test_glue_stack_config3_per_token_out_fc2():
     """BASELINE config 3 granularities (qkv / fc1 per-tensor, out / fc2 per-token): the producer-fused path keeps
     the norm->int8 and SwiGLU-epilogue fusions and must agree with the module path like the all-per-tensor case."""
