@@ -56,7 +56,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         compile_flags += ["-Xptxas", "-v"]
     jobs = []
     kernels_cu, glue_cu = SOURCES
+    with_mc = "-DASQ_ENABLE_MC" in compile_flags  # TUs 5 / 6: the 4-CTA multicast experiment (ASQ_MC=2), off by default
     for tu in range(N_KERNEL_TUS + 1):
+        if tu in (5, 6) and not with_mc:
+            continue
         obj = OBJ_DIR / f"asq_kernels_tu{tu}.o"
         jobs.append((obj, [nvcc, *compile_flags, f"-DASQ_TU={tu}", "-o", str(obj), str(kernels_cu)]))
     obj = OBJ_DIR / "asq_glue.o"

@@ -1826,11 +1826,11 @@ ASQ_LAUNCH_INST(true, 1, 1, asq::F_FULL)
 #if ASQ_TU == 0 || ASQ_TU == 4
 ASQ_LAUNCH_INST(true, 2, 1, asq::F_FULL)
 #endif
-#if ASQ_TU == 0 || ASQ_TU == 5
+#if defined(ASQ_ENABLE_MC) && (ASQ_TU == 0 || ASQ_TU == 5)
 ASQ_LAUNCH_INST(false, 2, 2, asq::F_FULL)
 ASQ_LAUNCH_DECL int max_multicast_clusters<false>(int);
 #endif
-#if ASQ_TU == 0 || ASQ_TU == 6
+#if defined(ASQ_ENABLE_MC) && (ASQ_TU == 0 || ASQ_TU == 6)
 ASQ_LAUNCH_INST(true, 2, 2, asq::F_FULL)
 ASQ_LAUNCH_DECL int max_multicast_clusters<true>(int);
 #endif
@@ -1925,7 +1925,11 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (mc_env < 0) { const char* e = getenv("ASQ_MC"); mc_env = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
     const int want = mc_env ? mc_env : 1;
     if (want == 2 && cg == 2 && p.N > asq::TILE_N && p.epi_kind != asq::EPI_SWIGLU && p.rope_cos == nullptr && p.ar_world <= 1 && p.group_of_blk == nullptr && p.batch_rows == 0) {
+#if defined(ASQ_ENABLE_MC) || !defined(ASQ_TU)
       const int clusters = fp8 ? max_multicast_clusters<true>(dev) : max_multicast_clusters<false>(dev);
+#else
+      const int clusters = 0;  // the 4-CTA multicast experiment (measured neutral) is compiled only with -DASQ_ENABLE_MC
+#endif
       const long long super_tiles = static_cast<long long>((p.M + tile_m - 1) / tile_m) * ((p.N + 2 * asq::TILE_N - 1) / (2 * asq::TILE_N));
       if (clusters > 0 && super_tiles >= clusters) mc = 2;
       if (mc == 2) mc_clusters = clusters;
@@ -2072,8 +2076,10 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   }
   const asq::PeerMapsT<false> none{};
   constexpr int FULL = asq::F_FULL;
+#if defined(ASQ_ENABLE_MC) || !defined(ASQ_TU)
   if (mc == 2) return fp8 ? launch_cfg<true, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
                           : launch_cfg<false, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+#endif
   if (fp8) {
     const char* lean = getenv("ASQ_LEAN");
     const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
