@@ -798,6 +798,8 @@ enum Feat : int {
   F_FULL = F_SK | F_GROUP | F_SWIGLU | F_ROPE | F_DEQ16 | F_OUT_ANY | F_PHASE1 | F_RESID,
 };
 
+constexpr int extra_kind(int feat) { return (feat & F_AR) ? 1 : ((feat & F_RESID) ? 2 : 0); }
+
 template <int FEAT>
 struct TileWalk {
   const LinearParams& p;
@@ -905,13 +907,18 @@ __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_re
 
 // Output maps of the other ranks' y buffers (all-reduce mode), in rank order skipping self.  Only the AR
 // instantiations of the kernel carry them: 896 bytes of launch parameters cost ~2 us per launch (measured).
-template <bool AR>
-struct PeerMapsT {
+// KIND 0: nothing; 1: the peers' y maps (all-reduce); 2: one map over the residual tensor (F_RESID without F_AR).
+template <int KIND>
+struct ExtraMapsT {
   char unused;
 };
 template <>
-struct PeerMapsT<true> {
+struct ExtraMapsT<1> {
   CUtensorMap m[7];
+};
+template <>
+struct ExtraMapsT<2> {
+  CUtensorMap m[1];
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -923,7 +930,7 @@ template <bool FP8, int CG, int MC, int FEAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmBu, const __grid_constant__ CUtensorMap tmY,
-                  const __grid_constant__ PeerMapsT<(FEAT & F_AR) != 0> tmPeers, const LinearParams p) {
+                  const __grid_constant__ ExtraMapsT<extra_kind(FEAT)> tmPeers, const LinearParams p) {
   constexpr bool AR = (FEAT & F_AR) != 0;
   constexpr bool kSK = (FEAT & F_SK) != 0, kGROUP = (FEAT & F_GROUP) != 0, kSWIGLU = (FEAT & F_SWIGLU) != 0;
   constexpr bool kROPE = (FEAT & F_ROPE) != 0, kDEQ16 = (FEAT & F_DEQ16) != 0, kOUT_ANY = (FEAT & F_OUT_ANY) != 0;
@@ -969,6 +976,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), NUM_EPI_WARPS * CG);  // epilogue warps of every CTA of the pair
     }
+    if ((FEAT & F_RESID) != 0 && (FEAT & F_AR) == 0)
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(bar_base + 8u * (2 * STAGES + 5 + w), 1);  // residual tile landed
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -1130,6 +1139,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 p.act_mode == ASQ_ACT_PER_TENSOR_DYNAMIC) &&
                                (p.epi_kind == EPI_DEQUANT || p.epi_kind == EPI_SWIGLU);
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
+    uint32_t resid_phase = 0;  // parity of this warp's residual-tile barrier
     // all-reduce mode: this launch's epoch = 1 + the epoch of the last launch that finished on this rank
     const uint32_t ar_epoch = (AR && p.ar_world > 1) ? __ldcg(p.ar_ctl[p.ar_rank]) + 1u : 0u;
     int it = 0;
@@ -1378,6 +1388,17 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
             __syncwarp();
           }
+          if constexpr (kRESID && !AR) {
+            if (p.residual != nullptr) {
+              const uint32_t rbar = bar_base + 8u * (2 * STAGES + 5 + ew);
+              if (lane == 0) {
+                mbar_arrive_expect_tx(rbar, EPI_BUF_BYTES);
+                tma_load_2d(buf, &tmPeers.m[0], rbar, col0 * elem, row0);  // 32 rows x 64 columns of the residual
+              }
+              mbar_wait(rbar, resid_phase);
+              resid_phase ^= 1u;
+            }
+          }
           tmem_ld_wait();
           float v[32];
           uint32_t w[16];
@@ -1410,15 +1431,16 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
             }
-            if (kRESID && p.residual != nullptr && row < p.M) {
-              // residual add in the activation dtype: T(res + T(v)), the eager `residual + linear(x)`
-              const int c0 = col0 + h * 32;
-              const uint16_t* rrow = reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.N + c0;
+            if constexpr (kRESID && !AR) {
+              if (p.residual != nullptr) {
+                // residual add in the activation dtype: T(res + T(v)), the eager `residual + linear(x)`.  The tile was
+                // TMA-loaded into this staging buffer (same 128B-swizzled layout as the output), so every lane
+                // reads its row's 16-byte pieces from shared memory; out-of-range elements are zero-filled.
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (c0 + 8 * q < p.N) {  // N % 8 == 0 (host-checked): a 16-byte piece is entirely in or out
-                  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(rrow) + q);
-                  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t aw[4];
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(aw[0]), "=r"(aw[1]), "=r"(aw[2]), "=r"(aw[3])
+                               : "r"(buf + lane * 128 + (((h * 4 + q) ^ (lane & 7)) << 4)));
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     float lo, hi, x0 = v[8 * q + 2 * i], x1 = v[8 * q + 2 * i + 1];
@@ -1726,7 +1748,7 @@ constexpr int kMaxDevices = 64;
 
 template <bool FP8, int CG, int MC, int FEAT>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBu, const CUtensorMap& tmY,
-               const asq::PeerMapsT<(FEAT & asq::F_AR) != 0>& tmPeers, const asq::LinearParams& p, int workers,
+               const asq::ExtraMapsT<asq::extra_kind(FEAT)>& tmPeers, const asq::LinearParams& p, int workers,
                cudaStream_t stream) {
   using Cfg = asq::TileCfg<CG>;
   auto kern = asq::asq_linear_kernel<FP8, CG, MC, FEAT>;
@@ -1802,7 +1824,7 @@ int max_multicast_clusters(int dev) {
 #define ASQ_LAUNCH_INST(FP8, CG, MC, FEAT)                                                                      \
   ASQ_LAUNCH_DECL int launch_cfg<FP8, CG, MC, FEAT>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,  \
                                                     const CUtensorMap&,                                          \
-                                                    const asq::PeerMapsT<((FEAT) & asq::F_AR) != 0>&,             \
+                                                    const asq::ExtraMapsT<asq::extra_kind(FEAT)>&,                \
                                                     const asq::LinearParams&, int, cudaStream_t);
 // lean instantiations for the launches of a Llama layer (int8, CTA pairs): see asq::Feat
 #define ASQ_LEAN_PLAIN (asq::F_DEQ16)
@@ -2058,7 +2080,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
   if (p.ar_world > 1) {
     if (!p.tma_store || peer_y == nullptr) return fail(ASQ_ERR_INVALID, "all-reduce mode needs a 16-byte aligned 16-bit output row pitch");
     if (fp8 || mc != 1) return fail(ASQ_ERR_UNSUPPORTED, "all-reduce mode exists for the int8 path only");
-    asq::PeerMapsT<true> tmPeers;
+    asq::ExtraMapsT<1> tmPeers;
     memset(&tmPeers, 0, sizeof(tmPeers));
     const long long row_bytes = static_cast<long long>(p.N) * 2;
     for (int i = 0; i < p.ar_world - 1; ++i) {
@@ -2074,11 +2096,19 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     return cg == 2 ? launch_cfg<false, 2, 1, asq::F_FULL | asq::F_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream)
                    : launch_cfg<false, 1, 1, asq::F_FULL | asq::F_AR>(tmA, tmB, tmBu, tmY, tmPeers, p, workers, stream);
   }
-  const asq::PeerMapsT<false> none{};
+  const asq::ExtraMapsT<0> none{};
+  asq::ExtraMapsT<2> resid;  // instantiations with F_RESID (the full kernel included) carry one map over the residual
+  memset(&resid, 0, sizeof(resid));
+  if (p.residual != nullptr) {
+    rc = make_tmap(&resid.m[0], p.residual, p.M, static_cast<long long>(p.N) * 2, 32);
+    if (rc != ASQ_OK) return rc;
+  } else {
+    resid.m[0] = tmA;  // unused, but must be a valid descriptor
+  }
   constexpr int FULL = asq::F_FULL;
 #if defined(ASQ_ENABLE_MC) || !defined(ASQ_TU)
-  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
-                          : launch_cfg<false, 2, 2, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  if (mc == 2) return fp8 ? launch_cfg<true, 2, 2, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream)
+                          : launch_cfg<false, 2, 2, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
 #endif
   if (fp8) {
     const char* lean = getenv("ASQ_LEAN");
@@ -2088,8 +2118,8 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
         p.epi_kind == asq::EPI_DEQUANT && p.tma_store && out16 && p.out_fq_scale == 0.f && p.dbg == nullptr &&
         p.act_mode != ASQ_ACT_PER_TENSOR_DYNAMIC && !(lean != nullptr && lean[0] == '0'))
       return launch_cfg<true, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
-    return cg == 2 ? launch_cfg<true, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream)
-                   : launch_cfg<true, 1, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    return cg == 2 ? launch_cfg<true, 2, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream)
+                   : launch_cfg<true, 1, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
   }
   if (cg == 2) {
     // What this launch needs; a lean instantiation is used when it covers exactly that (ASQ_LEAN=0 disables).
@@ -2111,14 +2141,14 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_SWIGLU)) return launch_cfg<false, 2, 1, ASQ_LEAN_SWIGLU>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_ROPE)) return launch_cfg<false, 2, 1, ASQ_LEAN_ROPE>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
-      if (need == (ASQ_LEAN_PLAIN_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_RESID>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
-      if (need == (ASQ_LEAN_PHASE1_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_RESID>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PLAIN_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_RESID>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
+      if (need == (ASQ_LEAN_PHASE1_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_RESID>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
       if (need == (ASQ_LEAN_PLAIN_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_PHASE1_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
     }
-    return launch_cfg<false, 2, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    return launch_cfg<false, 2, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
   }
-  return launch_cfg<false, 1, 1, FULL>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+  return launch_cfg<false, 1, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
 }
 
 int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t N, int64_t K) {
