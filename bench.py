@@ -468,8 +468,9 @@ def run_ours(args, cfg, layers):
                 **({"tp_reduce": args.tp_reduce} if args.parallel == "tp" and world > 1 else {}),
                 "projections": "q|k|v and gate|up fused per layer (4 GEMM launches/layer)"
                                if not args.no_fuse else "one launch per projection (7 launches/layer)",
-                "glue": ("add+RMSNorm->int8 and in-place RoPE kernels feed the GEMMs (asq_glue.cu); SiLU(gate)*up and "
-                         "down_proj's quantisation run in the gate|up GEMM epilogue; o_proj quantises in-kernel")
+                "glue": ("RMSNorm->int8 producer kernel (asq_glue.cu); RoPE in the q|k|v epilogue; SiLU(gate)*up and down_proj's "
+                         "quantisation in the gate|up epilogue; residual adds in the o_proj / down_proj epilogues; "
+                         "o_proj quantises in-kernel")
                         if getattr(model, "glue", False)
                         else "torch norms / RoPE / SiLU; every linear quantises its own input in-kernel",
                 "l2": "weights (6.6 GB int8) and activations stream through the 126 MB L2 every step: inputs larger than L2",
