@@ -1,6 +1,6 @@
 // asq_kernels.cu — B200 (sm_100a) SmoothQuant W8A8 / FP8 linear path: kernels + C ABI.
 //
-// One persistent, warp-specialised kernel per call (template: int8 | e4m3, N-tile width):
+// One persistent, warp-specialised kernel per call (template: int8 | e4m3, CTAs per tile, feature set):
 //
 //   phase 1 (epilogue warps, all CTAs)   x[M,K] (fp32|fp16|bf16) -> 8-bit A panel in an L2-resident
 //       workspace.  One warp per token row: per-token absmax with warp shuffles, true IEEE division,
@@ -10,7 +10,12 @@
 //       multi-stage mbarrier ring; one elected thread issues tcgen05.mma (kind::i8 -> int32,
 //       kind::f8f6f4 -> fp32) into a double-buffered TMEM accumulator; 8 epilogue warps drain TMEM
 //       with tcgen05.ld, apply the reference's fp32 dequant (+bias) arithmetic op for op, convert and
-//       store, overlapping the next tile's main loop.
+//       store through a swizzled staging tile + TMA store, overlapping the next tile's main loop.
+//
+// Epilogue / schedule variants of the same kernel (selected per launch, compiled per feature set — see Feat):
+// per-column scale vector (fused q|k|v, gate|up), SwiGLU (+ next layer's quantisation), RoPE, residual add,
+// raw int32 / alpha-beta / int8 outputs, stream-K tail, grouped (MoE experts) and batched weight selection,
+// and the row-parallel variant fused with its all-reduce over NVLink peer memory.
 //
 // Why the A operand takes one trip through L2 instead of being converted per CTA: every N-tile CTA
 // of an M panel would otherwise re-read the 16/32-bit activations and redo the division (N/BN times
