@@ -1746,7 +1746,7 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 
 // ---------------------------------------------------------------------- kernel launchers
 // The six instantiations of the kernel dominate the build time, so the build compiles this file once per
-// instantiation in parallel (-DASQ_TU=1..18: only the kernel + its launcher) plus once for the host side
+// instantiation in parallel (-DASQ_TU=1..20: only the kernel + its launcher) plus once for the host side
 // (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
 namespace asq_launch {
 constexpr int kMaxDevices = 64;
@@ -1896,6 +1896,14 @@ ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PLAIN_RESID)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 18
 ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_RESID)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 19
+ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_PLAIN)
+ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_PLAIN_SK)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 20
+ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_PHASE1)
+ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_PHASE1_SK)
 #endif
 #endif  // ASQ_TU
 }  // namespace asq_launch
@@ -2126,21 +2134,21 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     return cg == 2 ? launch_cfg<true, 2, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream)
                    : launch_cfg<true, 1, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
   }
+  // What this launch needs; a lean instantiation is used when it covers exactly that (ASQ_LEAN=0 disables).
+  static int lean_env = -1;
+  if (lean_env < 0) { const char* e = getenv("ASQ_LEAN"); lean_env = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
+  int need = 0;
+  if (p.x != nullptr) need |= asq::F_PHASE1;
+  if (p.sk_enabled) need |= asq::F_SK;
+  if (p.group_of_blk != nullptr || p.batch_rows > 0) need |= asq::F_GROUP;
+  if (p.epi_kind == asq::EPI_SWIGLU) need |= asq::F_SWIGLU;
+  else if (p.rope_cos != nullptr) need |= asq::F_ROPE;
+  else if (p.epi_kind == asq::EPI_DEQUANT && p.tma_store && out16 && p.out_fq_scale == 0.f) need |= asq::F_DEQ16;
+  else need |= asq::F_OUT_ANY;
+  if (p.residual != nullptr) need |= asq::F_RESID;
+  if (p.dbg != nullptr) need |= asq::F_OUT_ANY;  // timeline runs: always the full kernel
   if (cg == 2) {
-    // What this launch needs; a lean instantiation is used when it covers exactly that (ASQ_LEAN=0 disables).
-    static int lean_env = -1;
-    if (lean_env < 0) { const char* e = getenv("ASQ_LEAN"); lean_env = (e != nullptr && e[0] == '0') ? 0 : 1; }
-    const bool out16 = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
-    int need = 0;
-    if (p.x != nullptr) need |= asq::F_PHASE1;
-    if (p.sk_enabled) need |= asq::F_SK;
-    if (p.group_of_blk != nullptr || p.batch_rows > 0) need |= asq::F_GROUP;
-    if (p.epi_kind == asq::EPI_SWIGLU) need |= asq::F_SWIGLU;
-    else if (p.rope_cos != nullptr) need |= asq::F_ROPE;
-    else if (p.epi_kind == asq::EPI_DEQUANT && p.tma_store && out16 && p.out_fq_scale == 0.f) need |= asq::F_DEQ16;
-    else need |= asq::F_OUT_ANY;
-    if (p.residual != nullptr) need |= asq::F_RESID;
-    if (p.dbg != nullptr) need |= asq::F_OUT_ANY;  // timeline runs: always the full kernel
     if (lean_env) {
       if (need == (ASQ_LEAN_PLAIN)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
@@ -2152,6 +2160,13 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (need == (ASQ_LEAN_PHASE1_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
     }
     return launch_cfg<false, 2, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
+  }
+  // decode-sized launches (M <= 128, one CTA per tile): the same lean sets for the module forward and the int8-in entry
+  if (lean_env) {
+    if (need == (ASQ_LEAN_PLAIN)) return launch_cfg<false, 1, 1, ASQ_LEAN_PLAIN>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 1, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    if (need == (ASQ_LEAN_PLAIN_SK)) return launch_cfg<false, 1, 1, ASQ_LEAN_PLAIN_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+    if (need == (ASQ_LEAN_PHASE1_SK)) return launch_cfg<false, 1, 1, ASQ_LEAN_PHASE1_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
   }
   return launch_cfg<false, 1, 1, FULL>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
 }
