@@ -39,6 +39,7 @@
 
 #include "../../include/asq.h"
 #include "asq_ptx.cuh"
+#include "asq_smallm.h"
 
 namespace asq {
 
@@ -2185,6 +2186,13 @@ int check_common(const void* a, const void* w, const void* y, int64_t M, int64_t
 
 bool is_float_dtype(int d) { return d == ASQ_F32 || d == ASQ_F16 || d == ASQ_BF16; }
 
+// Decode-sized launches (M <= 16) take the weight-streaming kernel of asq_smallm.cu (ASQ_SMALLM=0 disables).
+bool smallm_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ASQ_SMALLM"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
 int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const float* bias, void* y, int y_dtype,
                  int64_t M, int64_t N, int64_t K, int act_mode, float quant_scale, float dequant_scale,
                  const float* col_scale, float* row_scale_out, int div_mode, void* workspace,
@@ -2210,6 +2218,26 @@ int fused_linear(bool fp8, const void* x, int x_dtype, const void* w, const floa
 
   Workspace ws;
   ws_layout(M, K, workspace, &ws);
+  if (!fp8 && residual == nullptr && out_fq_scale == 0.f && act_mode != ASQ_ACT_PER_TENSOR_DYNAMIC && smallm_enabled() &&
+      asq_smallm_supported(M, N, K, y_dtype)) {
+    // decode-sized M: stand-alone prologue into the workspace, then the weight-streaming kernel (two small launches)
+    const bool per_token = (act_mode == ASQ_ACT_PER_TOKEN || act_mode == ASQ_ACT_ROW_SCALE_GIVEN);
+    float* rs = per_token ? ws.row_scale : nullptr;
+    if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN) rs = row_scale_out;
+    rc = asq_quantize_act(x, x_dtype, ws.a_q, rs, M, K, act_mode, quant_scale, div_mode, 0, stream);
+    if (rc != ASQ_OK) return rc;
+    if (act_mode == ASQ_ACT_PER_TOKEN && row_scale_out != nullptr) {
+      cudaError_t e = cudaMemcpyAsync(row_scale_out, ws.row_scale, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToDevice,
+                                      static_cast<cudaStream_t>(stream));
+      if (e != cudaSuccess) return fail(ASQ_ERR_CUDA, "row scale copy failed: %s", cudaGetErrorString(e));
+    }
+    SmallMParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.xq = reinterpret_cast<const int8_t*>(ws.a_q); sp.w = static_cast<const int8_t*>(w); sp.row_scale = rs;
+    sp.col_scale = col_scale; sp.bias = bias; sp.y = y; sp.dequant_scale = dequant_scale;
+    sp.M = static_cast<int>(M); sp.N = static_cast<int>(N); sp.K = static_cast<int>(K); sp.y_dtype = y_dtype;
+    return asq_smallm_launch(sp, static_cast<cudaStream_t>(stream));
+  }
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.sync = ws.sync;
@@ -2321,6 +2349,14 @@ static int linear_q8_impl(const int8_t* xq, const float* row_scale, const int8_t
   int rc = check_common(xq, w, y, M, N, K);
   if (rc != ASQ_OK || M == 0) return rc;
   if (!is_float_dtype(y_dtype)) return fail(ASQ_ERR_INVALID, "y dtype must be f32, f16 or bf16");
+  if (residual == nullptr && smallm_enabled() && asq_smallm_supported(M, N, K, y_dtype)) {
+    SmallMParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.xq = xq; sp.w = w; sp.row_scale = row_scale; sp.col_scale = col_scale; sp.bias = bias; sp.y = y;
+    sp.dequant_scale = dequant_scale;
+    sp.M = static_cast<int>(M); sp.N = static_cast<int>(N); sp.K = static_cast<int>(K); sp.y_dtype = y_dtype;
+    return asq_smallm_launch(sp, static_cast<cudaStream_t>(stream));
+  }
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
   rc = attach_streamk(p, workspace, workspace_bytes);

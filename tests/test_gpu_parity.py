@@ -732,3 +732,36 @@ def test_i8bmm_family_vs_exact_integer_matmul(B, M, N, K):
     got8 = BMM_S8T_S8N_S8T(float(alpha8))(t(a), t(b))
     assert got8.dtype == torch.int8 and int(np.abs(want8).max()) > 50
     np.testing.assert_array_equal(got8.cpu().numpy(), want8)
+
+
+# ----------------------------------------------------------------------------- decode-sized M (weight-streaming kernel)
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+@pytest.mark.parametrize("M,N,K", [(1, 64, 256), (5, 4096, 4096), (16, 1024, 11008), (16, 12288, 4096), (9, 48, 512),
+                                   (17, 256, 1088), (33, 4096, 4096), (64, 512, 8192), (40, 64, 64)])
+def test_small_m_kernel_equals_tcgen05_kernel_and_oracle(dtype, M, N, K, exact_div):
+    """M <= 16 launches take asq_smallm.cu (mma.sync weight stream); rows are independent, so the same rows inside
+    a 96-row batch (tcgen05 kernel) must give identical bits; the smallest cases are also checked against the oracle.
+    The M > 16 cases pin the hand-over back to the tcgen05 kernel."""
+    rng = np.random.default_rng(M * N + K)
+    td = TORCH_DT[dtype]
+    x = make_x(rng, 96, K, dtype, 1.0)
+    w = rng.integers(-127, 128, size=(N, K), dtype=np.int8)
+    b = rng.standard_normal(N).astype(np.float32)
+    cs = (rng.random(N).astype(np.float32) + 0.5) * 2e-4
+    xt, wt, bt, cst = t(x, td), t(w), t(b), t(cs)
+    for mode, qs in ((L.ACT_ROUND, 1.0), (L.ACT_SCALE, 0.0473), (L.ACT_PER_TOKEN, 1.0)):
+        scale = 40.0 if mode == L.ACT_ROUND else 1.0
+        xs = (xt.float() * scale).to(td)
+        big = L.w8a8_linear(xs, wt, bt, mode, qs, 3.1e-4)
+        small = L.w8a8_linear(xs[:M].contiguous(), wt, bt, mode, qs, 3.1e-4)
+        assert torch.equal(small, big[:M]), f"mode {mode}: {(small != big[:M]).sum().item()} elements differ"
+        big_cs = L.w8a8_linear(xs, wt, None, mode, qs, 1.0, col_scale=cst)
+        small_cs = L.w8a8_linear(xs[:M].contiguous(), wt, None, mode, qs, 1.0, col_scale=cst)
+        assert torch.equal(small_cs, big_cs[:M])
+    q, s = L.quantize_act(xt, L.ACT_PER_TOKEN)
+    assert torch.equal(L.w8a8_linear_q8(q[:M].contiguous(), wt, bt, 3.1e-4, row_scale=s[:M].contiguous(), out_dtype=td),
+                       L.w8a8_linear_q8(q, wt, bt, 3.1e-4, row_scale=s, out_dtype=td)[:M])
+    if N * K <= 64 * 512:
+        want = O.w8a8_linear(x[:M], dtype, w, 3.1e-4, act_quant="per-token", bias=b, div_mode="exact")
+        got = L.w8a8_linear(xt[:M].contiguous(), wt, bt, L.ACT_PER_TOKEN, 1.0, 3.1e-4)
+        np.testing.assert_array_equal(got.float().cpu().numpy(), want)
