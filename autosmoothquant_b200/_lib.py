@@ -47,6 +47,8 @@ EXPORTED_SYMBOLS = (
     "asq_w8a8_gateup_swiglu_q8",
     "asq_w8a8_linear_q8_rope",
     "asq_w8a8_linear_res",
+    "asq_w8a8_rmsnorm_linear_rope",
+    "asq_w8a8_rmsnorm_gateup_swiglu",
     "asq_w8a8_linear_q8_res",
     "asq_w8a8_grouped_linear",
     "asq_i8bmm",
@@ -129,6 +131,12 @@ def load():
         lib.asq_w8a8_gateup_swiglu_q8.restype = c_i
         lib.asq_w8a8_gateup_swiglu_q8.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i64, c_i64, c_i64, c_f, c_f,
                                                   c_vp, c_f, c_i, c_vp]
+        lib.asq_w8a8_rmsnorm_linear_rope.restype = c_i
+        lib.asq_w8a8_rmsnorm_linear_rope.argtypes = [c_vp, c_i, c_vp, c_f, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f, c_vp,
+                                                     c_vp, c_vp, c_i64, c_i64, c_i64, c_i, c_vp, c_sz, c_vp]
+        lib.asq_w8a8_rmsnorm_gateup_swiglu.restype = c_i
+        lib.asq_w8a8_rmsnorm_gateup_swiglu.argtypes = [c_vp, c_i, c_vp, c_f, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f, c_f,
+                                                       c_vp, c_f, c_i, c_vp, c_sz, c_vp]
         lib.asq_w8a8_linear_res.restype = c_i
         lib.asq_w8a8_linear_res.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f,
                                             c_vp, c_vp, c_i, c_vp, c_sz, c_vp]
@@ -499,6 +507,91 @@ def rope_tables_blocked(table: torch.Tensor) -> torch.Tensor:
     """[S, head_dim] cos or sin table -> the [head_dim/8, S, 8] layout the RoPE epilogue reads (one-time re-layout)."""
     S, hd = table.shape
     return table.reshape(S, hd // 8, 8).transpose(0, 1).contiguous()
+
+
+def w8a8_rmsnorm_linear(
+    x: torch.Tensor,
+    norm_weight: torch.Tensor,
+    eps: float,
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    dequant_scale: float = 1.0,
+    col_scale: Optional[torch.Tensor] = None,
+    rope: Optional[tuple] = None,
+) -> torch.Tensor:
+    """RMSNorm (folded scale) -> round-only int8 -> GEMM -> dequant [-> RoPE] in ONE launch; x [M,K] f16 | bf16.
+    rope as in w8a8_linear_q8.  Bit-identical to add_rmsnorm_quant(x, None, ...) followed by w8a8_linear_q8."""
+    global _launches
+    dev = _require_cuda(x, norm_weight, weight, bias, col_scale)
+    if x.dim() != 2 or weight.dtype != torch.int8 or x.shape[1] != weight.shape[1] or norm_weight.dtype != x.dtype:
+        raise ValueError("w8a8_rmsnorm_linear expects x [M,K] (16-bit), a [K] norm weight of the same dtype and int8 [N,K] weights")
+    if not (x.is_contiguous() and weight.is_contiguous() and norm_weight.is_contiguous()):
+        raise ValueError("w8a8_rmsnorm_linear expects contiguous tensors")
+    M, K = x.shape
+    N = weight.shape[0]
+    y = torch.empty((M, N), dtype=x.dtype, device=dev)
+    if M == 0:
+        return y
+    cos = sin = None
+    S = rope_cols = hd = 0
+    dup = False
+    if rope is not None:
+        cos, sin, S, rope_cols = rope[:4]
+        dup = bool(rope[4]) if len(rope) > 4 else False
+        _require_cuda(cos, sin)
+        if cos.dtype != x.dtype or sin.dtype != x.dtype or cos.shape != sin.shape or cos.dim() != 3 or cos.shape[1] != S or cos.shape[2] != 8:
+            raise ValueError("rope tables must be rope_tables_blocked() outputs [head_dim/8, S, 8] of the activation dtype")
+        hd = cos.shape[0] * 8
+    lib = load()
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(M, K))
+        rc = lib.asq_w8a8_rmsnorm_linear_rope(x.data_ptr(), _code(x.dtype), norm_weight.data_ptr(), float(eps), weight.data_ptr(),
+                                              _ptr(bias), y.data_ptr(), M, N, K, float(dequant_scale), _ptr(col_scale),
+                                              _ptr(cos), _ptr(sin), int(S), int(rope_cols), int(hd), 1 if dup else 0, ws, ws_bytes, stream)
+    _check(rc)
+    _launches += 1
+    return y
+
+
+def w8a8_rmsnorm_gateup_swiglu(
+    x: torch.Tensor,
+    norm_weight: torch.Tensor,
+    eps: float,
+    weight_il: torch.Tensor,
+    bias_il: Optional[torch.Tensor],
+    dequant_scale: float = 1.0,
+    up_dequant_scale: Optional[float] = None,
+    col_scale_il: Optional[torch.Tensor] = None,
+    out_quant_scale: Optional[float] = None,
+    div_mode: Optional[int] = None,
+) -> torch.Tensor:
+    """RMSNorm -> int8 -> gate|up GEMM -> SwiGLU (-> down_proj's int8) in ONE launch; see w8a8_gateup_swiglu."""
+    global _launches
+    dev = _require_cuda(x, norm_weight, weight_il, bias_il, col_scale_il)
+    if x.dim() != 2 or weight_il.dtype != torch.int8 or x.shape[1] != weight_il.shape[1] or norm_weight.dtype != x.dtype:
+        raise ValueError("w8a8_rmsnorm_gateup_swiglu expects x [M,K] (16-bit), a [K] norm weight and int8 [2I,K] weights")
+    if not (x.is_contiguous() and weight_il.is_contiguous() and norm_weight.is_contiguous()):
+        raise ValueError("w8a8_rmsnorm_gateup_swiglu expects contiguous tensors")
+    M, K = x.shape
+    N = weight_il.shape[0]
+    out_dtype = torch.int8 if out_quant_scale is not None else x.dtype
+    out = torch.empty((M, N // 2), dtype=out_dtype, device=dev)
+    if M == 0:
+        return out
+    lib = load()
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        ws, ws_bytes = _workspace(dev, stream, lib.asq_workspace_bytes(M, K))
+        rc = lib.asq_w8a8_rmsnorm_gateup_swiglu(
+            x.data_ptr(), _code(x.dtype), norm_weight.data_ptr(), float(eps), weight_il.data_ptr(), _ptr(bias_il), out.data_ptr(),
+            _code(out_dtype), M, N, K, float(dequant_scale),
+            float(dequant_scale if up_dequant_scale is None else up_dequant_scale), _ptr(col_scale_il),
+            float(out_quant_scale) if out_quant_scale is not None else 0.0,
+            _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream)
+    _check(rc)
+    _launches += 1
+    return out
 
 
 def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:

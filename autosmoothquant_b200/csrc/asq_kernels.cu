@@ -82,6 +82,10 @@ struct LinearParams {
   // EPI_SWIGLU: w rows interleave 32 gate rows with the 32 matching up rows; the epilogue emits
   // a = T(T(silu(gate)) * up) as T (y_dtype 16-bit) or sat(rint(T(a / out_quant_scale))) as int8, [M, N/2]
   float out_quant_scale, inv_out_quant_scale;
+  // ASQ_ACT_RMSNORM: phase 1 is HF RMSNorm (+ the folded 1/input_scale) followed by round-only quantisation:
+  // q = sat(rint(T(norm_weight * T(x * rsqrt(mean(x^2) + eps))))), the arithmetic of asq_add_rmsnorm_quant
+  const void* norm_weight;  // [K] of x's dtype
+  float norm_eps;
   // y = T(residual + T(linear output)): the residual-stream add of the decoder block (HF LlamaDecoderLayer:
   // hidden = residual + o_proj(...) / + down_proj(...)) in the epilogue, so the following norm kernel reads one
   // tensor instead of two and writes no copy of the stream.  [M, N] of y's 16-bit dtype, may alias y.
@@ -379,12 +383,80 @@ __device__ __forceinline__ float quantize_row(const T* __restrict__ xrow, uint8_
   return (QM == QM_ROW_DIV || QM == QM_TENSOR_DYN) ? scale : 0.f;  // QM_SCALE_*: `scale` carried 1/qs or qs, not a row scale
 }
 
+// RMSNorm + round-only quantisation of one row by one warp (ASQ_ACT_RMSNORM).  Bit-identical to the stand-alone
+// asq_add_rmsnorm_quant kernel (asq_glue.cu): that kernel gives vector v of a row to thread v % 128 of a 128-thread
+// CTA, sums squares per thread with fmaf in ascending order, reduces every warp with an xor-shuffle tree and adds
+// the four warp sums left to right.  Lane l of this warp holds vectors l + 32 m, i.e. those of the virtual
+// threads l + 32 w with w = m % 4: four partial sums per lane, four shuffle trees, the same final order.
+template <typename T>
+__device__ __forceinline__ float quantize_row_rmsnorm(const T* __restrict__ xrow, uint8_t* __restrict__ qrow, int K, int lane,
+                                                      const LinearParams& p) {
+  constexpr int VEC = Elem<T>::VEC;
+  static_assert(VEC == 8, "RMSNorm prologue: 16-bit activations only");
+  constexpr int STEP = 32 * VEC;
+  constexpr int CHUNK = STEP * QBATCH;  // 4096 elements = 16 vectors per lane: (chunk start / STEP) % 4 == 0
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const T* wv = reinterpret_cast<const T*>(p.norm_weight);
+  float ssw[4] = {0.f, 0.f, 0.f, 0.f};
+  uint4 buf[QBATCH];
+  for (int c0 = 0; c0 < K; c0 += CHUNK) {
+#pragma unroll
+    for (int j = 0; j < QBATCH; ++j) {
+      const int c = c0 + lane * VEC + j * STEP;
+      buf[j] = (c < K) ? __ldg(reinterpret_cast<const uint4*>(xrow + c)) : zero;
+    }
+#pragma unroll
+    for (int j = 0; j < QBATCH; ++j) {
+      if (c0 + lane * VEC + j * STEP < K) {
+        float f[VEC];
+        Elem<T>::unpack(buf[j], f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) ssw[j & 3] = fmaf(f[i], f[i], ssw[j & 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssw[w] += __shfl_xor_sync(0xffffffffu, ssw[w], o);
+  const float ss = ssw[0] + ssw[1] + ssw[2] + ssw[3];
+  const float rstd = rsqrtf(ss / static_cast<float>(K) + p.norm_eps);
+  for (int c0 = 0; c0 < K; c0 += CHUNK) {
+    if (K > CHUNK) {  // a long row does not fit the registers: second read (L2)
+#pragma unroll
+      for (int j = 0; j < QBATCH; ++j) {
+        const int c = c0 + lane * VEC + j * STEP;
+        buf[j] = (c < K) ? __ldg(reinterpret_cast<const uint4*>(xrow + c)) : zero;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < QBATCH; ++j) {
+      const int c = c0 + lane * VEC + j * STEP;
+      if (c < K) {
+        float f[VEC], g[VEC];
+        Elem<T>::unpack(buf[j], f);
+        Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(wv + c)), g);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) f[i] = Elem<T>::round_to(__fmul_rn(g[i], Elem<T>::round_to(__fmul_rn(f[i], rstd))));
+        pack_store<false, VEC>(qrow + c, f);
+      }
+    }
+  }
+  return 0.f;
+}
+template <>
+__device__ __forceinline__ float quantize_row_rmsnorm<float>(const float*, uint8_t*, int, int, const LinearParams&) {
+  return 0.f;  // rejected on the host: the norm runs in a 16-bit activation dtype
+}
+
 template <typename T, bool FP8>
 __device__ __forceinline__ float quantize_row_typed(const LinearParams& p, int row, int lane, float tensor_scale) {
   const size_t off = static_cast<size_t>(row) * p.K;
   const T* xrow = reinterpret_cast<const T*>(p.x) + off;
   uint8_t* qrow = p.a_q + off;
   switch (p.act_mode) {  // warp-uniform: one branch per row, straight-line code per vector
+    case ASQ_ACT_RMSNORM:
+      return FP8 ? 0.f : quantize_row_rmsnorm<T>(xrow, qrow, p.K, lane, p);
     case ASQ_ACT_PER_TOKEN:
       return quantize_row<T, FP8, QM_ROW_DIV>(xrow, qrow, p.K, lane, p, 0.f, true);
     case ASQ_ACT_ROW_SCALE_GIVEN:
@@ -1747,7 +1819,7 @@ size_t ws_layout(int64_t M, int64_t K, void* base, Workspace* w) {
 
 // ---------------------------------------------------------------------- kernel launchers
 // The six instantiations of the kernel dominate the build time, so the build compiles this file once per
-// instantiation in parallel (-DASQ_TU=1..20: only the kernel + its launcher) plus once for the host side
+// instantiation in parallel (-DASQ_TU=1..22: only the kernel + its launcher) plus once for the host side
 // (-DASQ_TU=0: everything else, launchers declared `extern template`).  Without ASQ_TU it is one ordinary TU.
 namespace asq_launch {
 constexpr int kMaxDevices = 64;
@@ -1842,6 +1914,8 @@ int max_multicast_clusters(int dev) {
 #define ASQ_LEAN_PHASE1_SK (asq::F_DEQ16 | asq::F_PHASE1 | asq::F_SK)
 #define ASQ_LEAN_PLAIN_RESID (asq::F_DEQ16 | asq::F_RESID)
 #define ASQ_LEAN_PHASE1_RESID (asq::F_DEQ16 | asq::F_PHASE1 | asq::F_RESID)
+#define ASQ_LEAN_PHASE1_ROPE (asq::F_ROPE | asq::F_PHASE1)
+#define ASQ_LEAN_PHASE1_SWIGLU (asq::F_SWIGLU | asq::F_PHASE1)
 #if ASQ_TU == 0 || ASQ_TU == 1
 ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL)
 #endif
@@ -1897,6 +1971,12 @@ ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PLAIN_RESID)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 18
 ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_RESID)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 21
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_ROPE)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 22
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_SWIGLU)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 19
 ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_PLAIN)
@@ -2155,6 +2235,8 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (need == (ASQ_LEAN_PHASE1)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_SWIGLU)) return launch_cfg<false, 2, 1, ASQ_LEAN_SWIGLU>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_ROPE)) return launch_cfg<false, 2, 1, ASQ_LEAN_ROPE>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PHASE1_ROPE)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_ROPE>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
+      if (need == (ASQ_LEAN_PHASE1_SWIGLU)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_SWIGLU>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
       if (need == (ASQ_LEAN_PLAIN_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_RESID>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
       if (need == (ASQ_LEAN_PHASE1_RESID)) return launch_cfg<false, 2, 1, ASQ_LEAN_PHASE1_RESID>(tmA, tmB, tmBu, tmY, resid, p, workers, stream);
       if (need == (ASQ_LEAN_PLAIN_SK)) return launch_cfg<false, 2, 1, ASQ_LEAN_PLAIN_SK>(tmA, tmB, tmBu, tmY, none, p, workers, stream);
@@ -2291,6 +2373,76 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
   const float ds = (act_mode == ASQ_ACT_SCALE) ? w_scale * in_scale : w_scale;
   return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, in_scale, ds, nullptr,
                       row_scale_out, div_mode, workspace, workspace_bytes, stream, out_scale);
+}
+
+// ---- RMSNorm as the prologue of the q|k|v and gate|up launches (the norm kernel disappears from the layer)
+namespace {
+int prep_rmsnorm_prologue(asq::LinearParams& p, const void* x, int x_dtype, const void* norm_weight, float eps, int64_t M,
+                          int64_t K, void* workspace, size_t workspace_bytes) {
+  if (x_dtype != ASQ_BF16 && x_dtype != ASQ_F16) return fail(ASQ_ERR_INVALID, "rmsnorm prologue: x dtype must be f16 or bf16");
+  if (norm_weight == nullptr || (reinterpret_cast<uintptr_t>(norm_weight) & 15) || K % 8 != 0)
+    return fail(ASQ_ERR_INVALID, "rmsnorm prologue: norm weight must be a 16-byte aligned [K] vector, K %% 8 == 0");
+  if ((M + asq::BLOCK_M - 1) / asq::BLOCK_M + 1 > static_cast<int64_t>(kSyncBytes / 4) - 2)
+    return fail(ASQ_ERR_UNSUPPORTED, "M=%lld exceeds the row panels one launch tracks; split the batch", (long long)M);
+  if (workspace == nullptr || workspace_bytes < asq_workspace_bytes(M, K))
+    return fail(ASQ_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", asq_workspace_bytes(M, K), workspace_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(ASQ_ERR_INVALID, "workspace must be 1024-byte aligned");
+  Workspace ws;
+  ws_layout(M, K, workspace, &ws);
+  p.x = x; p.x_dtype = x_dtype; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.sync = ws.sync;
+  p.act_mode = ASQ_ACT_RMSNORM; p.norm_weight = norm_weight; p.norm_eps = eps;
+  p.quant_scale = 1.f; p.inv_quant_scale = 1.f; p.qmax = 127.0f; p.inv_qmax = 1.0f / 127.0f;
+  return ASQ_OK;
+}
+}  // namespace
+
+int asq_w8a8_rmsnorm_linear_rope(const void* x, int x_dtype, const void* norm_weight, float eps, const int8_t* w,
+                                 const float* bias, void* y, int64_t M, int64_t N, int64_t K, float dequant_scale,
+                                 const float* col_scale, const void* cos_table, const void* sin_table, int64_t S,
+                                 int64_t rope_cols, int64_t head_dim, int halves_equal, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, w, y, M, N, K);
+  if (rc != ASQ_OK || M == 0) return rc;
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  rc = prep_rmsnorm_prologue(p, x, x_dtype, norm_weight, eps, M, K, workspace, workspace_bytes);
+  if (rc != ASQ_OK) return rc;
+  if (cos_table != nullptr) {
+    if (head_dim != 128) return fail(ASQ_ERR_UNSUPPORTED, "rope epilogue: head_dim %lld (only 128)", (long long)head_dim);
+    if (N % 128 != 0 || rope_cols % 128 != 0 || rope_cols < 0 || rope_cols > N || S <= 0 || S > 0x7fffffffLL || sin_table == nullptr ||
+        (reinterpret_cast<uintptr_t>(cos_table) & 15) || (reinterpret_cast<uintptr_t>(sin_table) & 15))
+      return fail(ASQ_ERR_INVALID, "rope epilogue: bad table / column arguments");
+    p.rope_cos = cos_table; p.rope_sin = sin_table; p.rope_S = static_cast<int>(S); p.rope_cols = static_cast<int>(rope_cols);
+    p.rope_halves_equal = halves_equal ? 1 : 0;
+  }
+  p.y = y; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = x_dtype; p.epi_kind = asq::EPI_DEQUANT;
+  return launch_linear(false, p.a_q, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int asq_w8a8_rmsnorm_gateup_swiglu(const void* x, int x_dtype, const void* norm_weight, float eps, const int8_t* w_il,
+                                   const float* bias_il, void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
+                                   float gate_dequant_scale, float up_dequant_scale, const float* col_scale_il,
+                                   float out_quant_scale, int div_mode, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  int rc = check_common(x, w_il, out, M, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (N % 64 != 0) return fail(ASQ_ERR_INVALID, "swiglu: N=%lld (2 x intermediate) must be a multiple of 64", (long long)N);
+  if (out_dtype != ASQ_I8 && out_dtype != x_dtype) return fail(ASQ_ERR_INVALID, "swiglu: out_dtype must be i8 or equal x's dtype");
+  if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
+  if (out_dtype == ASQ_I8 && !(out_quant_scale > 0.f)) return fail(ASQ_ERR_INVALID, "swiglu: out_quant_scale must be positive");
+  if (M == 0) return ASQ_OK;
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  rc = prep_rmsnorm_prologue(p, x, x_dtype, norm_weight, eps, M, K, workspace, workspace_bytes);
+  if (rc != ASQ_OK) return rc;
+  p.y = out; p.bias = bias_il; p.col_scale = col_scale_il;
+  p.dequant_scale = gate_dequant_scale; p.dequant_scale_up = up_dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = out_dtype; p.mid_dtype = x_dtype; p.epi_kind = asq::EPI_SWIGLU; p.div_mode = div_mode;
+  p.out_quant_scale = out_quant_scale; p.inv_out_quant_scale = out_dtype == ASQ_I8 ? 1.0f / out_quant_scale : 0.f;
+  return launch_linear(false, p.a_q, w_il, p, static_cast<cudaStream_t>(stream));
 }
 
 int asq_w8a8_linear_q8_rope(const int8_t* xq, const float* row_scale, const int8_t* w, const float* bias, void* y,

@@ -249,13 +249,22 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     # residual add inside the o_proj / down_proj epilogues (the residual tile is TMA-loaded into the staging buffer):
     # bit-identical, the norm kernels then read one tensor and write no copy of the stream; 12.86 vs 13.02-13.10 ms
     fuse_res = getattr(layer, "tp_world", 1) == 1 and os.environ.get("ASQ_RESIDUAL_EPILOGUE", "1") != "0"
-    x2, _, q8 = _lib.add_rmsnorm_quant(x2, delta, layer.input_layernorm_weight, cfg.rms_eps)
+    # RMSNorm as the prologue of the q|k|v / gate|up launches (needs the residual already added: delta is None).
+    # Bit-identical and 64 launches fewer per step, but measured SLOWER (13.9 vs 13.0 ms): the prologue runs while
+    # the tensor cores of that launch idle (~8 us per launch), the stand-alone norm kernel costs ~5 us -> opt-in
+    norm_prologue = fuse_res and os.environ.get("ASQ_NORM_PROLOGUE", "0") == "1"
     qkv_mod = layer.qkv_proj
     nq, nk, nv = (n // hd for n in layer.qkv_sizes)
     rope_in_epilogue = hd == 128 and os.environ.get("ASQ_ROPE_EPILOGUE", "1") != "0"
-    qkv = _lib.w8a8_linear_q8(q8, qkv_mod.weight, qkv_mod.bias if qkv_mod.use_bias else None, 1.0,
-                              col_scale=qkv_mod._col_scale(x2.device), out_dtype=x2.dtype,
-                              rope=_rope_arg(cos, sin, S, (nq + nk) * hd) if rope_in_epilogue else None)
+    rope_arg = _rope_arg(cos, sin, S, (nq + nk) * hd) if rope_in_epilogue else None
+    if norm_prologue and delta is None:
+        qkv = _lib.w8a8_rmsnorm_linear(x2, layer.input_layernorm_weight, cfg.rms_eps, qkv_mod.weight,
+                                       qkv_mod.bias if qkv_mod.use_bias else None, 1.0,
+                                       col_scale=qkv_mod._col_scale(x2.device), rope=rope_arg)
+    else:
+        x2, _, q8 = _lib.add_rmsnorm_quant(x2, delta, layer.input_layernorm_weight, cfg.rms_eps)
+        qkv = _lib.w8a8_linear_q8(q8, qkv_mod.weight, qkv_mod.bias if qkv_mod.use_bias else None, 1.0,
+                                  col_scale=qkv_mod._col_scale(x2.device), out_dtype=x2.dtype, rope=rope_arg)
     if not rope_in_epilogue:
         _lib.rope_inplace(qkv, cos, sin, S, nq + nk, hd)
     q, k, v = qkv.split(layer.qkv_sizes, dim=-1)
@@ -283,10 +292,22 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
         o = None
     else:
         o = layer.o_proj(attn2)
-    x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
     tp_world = getattr(layer, "tp_world", 1)
     down = layer.down_proj.shard if tp_world > 1 else layer.down_proj
     il = getattr(layer, "gate_up_il", None)
+    if norm_prologue and o is None and il is not None:
+        per_token_down = down.act_quant == "per-token"
+        a = _lib.w8a8_rmsnorm_gateup_swiglu(x2, layer.post_attention_layernorm_weight, cfg.rms_eps, il[0], il[1], il[2],
+                                            up_dequant_scale=il[3],
+                                            out_quant_scale=None if per_token_down else float(down.quant_scale.item()))
+        if per_token_down:
+            x2 = _lib.w8a8_linear(a, down.weight, down.bias if down.use_bias else None, _lib.ACT_PER_TOKEN, 1.0,
+                                  float(down.dequant_scale.item()), residual=x2)
+        else:
+            x2 = _lib.w8a8_linear_q8(a, down.weight, down.bias if down.use_bias else None, float(down.dequant_scale.item()),
+                                     out_dtype=x2.dtype, residual=x2)
+        return x2, None
+    x2, _, q8 = _lib.add_rmsnorm_quant(x2, o, layer.post_attention_layernorm_weight, cfg.rms_eps)
     if down.act_quant == "per-token":
         # per-token fc2: the row absmax needs the whole SiLU*up row, so the epilogue emits the product in the
         # activation dtype and down_proj (module / row-parallel wrapper) quantises it per token in its own launch

@@ -74,8 +74,10 @@ typedef enum asq_act_mode {
   ASQ_ACT_SCALE = 1,
   ASQ_ACT_PER_TOKEN = 2,
   ASQ_ACT_PER_TENSOR_DYNAMIC = 3,
-  ASQ_ACT_ROW_SCALE_GIVEN = 4 /* per-token arithmetic with caller-supplied scales s[m] (row-parallel
-                                 tensor parallelism: the global row absmax is all-reduced first) */
+  ASQ_ACT_ROW_SCALE_GIVEN = 4, /* per-token arithmetic with caller-supplied scales s[m] (row-parallel
+                                  tensor parallelism: the global row absmax is all-reduced first) */
+  ASQ_ACT_RMSNORM = 5          /* (asq_w8a8_rmsnorm_* entry points) HF RMSNorm with the folded 1/input_scale as the
+                                  prologue: q = sat(rint(T(norm_w * T(x * rsqrt(mean(x^2) + eps)))))  models/llama.py:27-37 */
 } asq_act_mode;
 
 /* How `tensor / python_scalar` is evaluated.  torch on CUDA multiplies by the
@@ -174,6 +176,22 @@ int asq_w8a8_linear_q8_rope(const int8_t* xq, const float* row_scale, const int8
                             float dequant_scale, const float* col_scale,
                             const void* cos_table, const void* sin_table, int64_t S, int64_t rope_cols,
                             int64_t head_dim, int halves_equal, void* stream);
+
+/* The q|k|v and gate|up launches with the preceding RMSNorm as their prologue (ASQ_ACT_RMSNORM): x [M,K] is the
+ * residual stream (F16 | BF16), norm_weight [K] the norm weight with 1/input_scale folded in (models/llama.py:
+ * 27-37, 326-339); q = sat(rint(T(norm_weight * T(x * rsqrt(mean(x^2) + eps))))) feeds the GEMM, bit-identical to
+ * asq_add_rmsnorm_quant followed by the int8-in entry points.  Epilogues as in asq_w8a8_linear_q8_rope (cos_table
+ * NULL: plain dequant, y in x's dtype) and asq_w8a8_gateup_swiglu_q8.  Workspace as for asq_w8a8_linear. */
+int asq_w8a8_rmsnorm_linear_rope(const void* x, int x_dtype, const void* norm_weight, float eps, const int8_t* w,
+                                 const float* bias, void* y, int64_t M, int64_t N, int64_t K, float dequant_scale,
+                                 const float* col_scale, const void* cos_table, const void* sin_table, int64_t S,
+                                 int64_t rope_cols, int64_t head_dim, int halves_equal, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int asq_w8a8_rmsnorm_gateup_swiglu(const void* x, int x_dtype, const void* norm_weight, float eps, const int8_t* w_il,
+                                   const float* bias_il, void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
+                                   float gate_dequant_scale, float up_dequant_scale, const float* col_scale_il,
+                                   float out_quant_scale, int div_mode, void* workspace, size_t workspace_bytes,
+                                   void* stream);
 
 /* gate|up projection with the SwiGLU product (and the next Linear's activation quantisation) in the GEMM
  * epilogue: the [M, 2I] gate|up tensor of HF LlamaMLP.forward (borrowed at models/llama.py:218) never

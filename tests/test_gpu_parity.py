@@ -558,6 +558,59 @@ def test_residual_epilogue_equals_linear_then_add(dtype, M, N, K, exact_div):
     assert rc == 0 and torch.equal(inplace, got)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,K,nh,I", [(300, 256, 2, 96), (2048, 4096, 4, 512), (130, 5120, 1, 64), (64, 1008, 1, 32)])
+def test_rmsnorm_prologue_equals_norm_kernel_then_int8_entry(dtype, M, K, nh, I):
+    """RMSNorm as the prologue of the q|k|v (+RoPE) and gate|up (+SwiGLU) launches == asq_add_rmsnorm_quant followed by
+    the int8-in entry points, bit for bit (the prologue reproduces the norm kernel's reduction order).  K = 5120
+    exercises the two-pass path of rows longer than one register batch, K = 1008 a ragged last vector group."""
+    if M == 2048 and dtype == "f16":
+        pytest.skip("full-size case runs once")
+    td = TORCH_DT[dtype]
+    g = torch.Generator().manual_seed(M + K)
+    x = (torch.randn(M, K, generator=g) * 1.7).to(td).to(DEV)
+    nw = ((torch.rand(K, generator=g) + 0.5) * 25.0).to(td).to(DEV)  # norm weight with a folded 1/input_scale
+    eps = 1e-5
+    hd = 128
+    N = 3 * nh * hd
+    wq = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    cs = (torch.rand(N, generator=g) * 2e-5 + 1e-5).to(DEV)
+    S = M
+    ang = torch.outer(torch.arange(S, dtype=torch.float32), 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd)))
+    emb = torch.cat([ang, ang], dim=-1)
+    rope = (L.rope_tables_blocked(emb.cos().to(td).to(DEV)), L.rope_tables_blocked(emb.sin().to(td).to(DEV)), S, 2 * nh * hd, True)
+    _, _, q8 = L.add_rmsnorm_quant(x, None, nw, eps)
+    assert int(q8.abs().max()) > 60
+    for r in (None, rope):
+        want = L.w8a8_linear_q8(q8, wq, b, 1.0, col_scale=cs, out_dtype=td, rope=r)
+        got = L.w8a8_rmsnorm_linear(x, nw, eps, wq, b, 1.0, col_scale=cs, rope=r)
+        assert torch.equal(got, want), f"rope={r is not None}: {(got != want).sum().item()} elements differ"
+    wg = torch.randint(-127, 128, (I, K), dtype=torch.int8, generator=g).to(DEV)
+    wu = torch.randint(-127, 128, (I, K), dtype=torch.int8, generator=g).to(DEV)
+    w_il = L.interleave_gate_up(wg, wu)
+    sc = 3e-6 * (4096 / K) ** 0.5
+    for qs in (0.0431, None):
+        want = L.w8a8_gateup_swiglu(q8, w_il, None, sc, up_dequant_scale=1.4 * sc, out_quant_scale=qs, mid_dtype=td)
+        got = L.w8a8_rmsnorm_gateup_swiglu(x, nw, eps, w_il, None, sc, up_dequant_scale=1.4 * sc, out_quant_scale=qs)
+        assert torch.equal(got, want)
+
+
+def test_glue_stack_norm_prologue_is_bit_identical(monkeypatch):
+    from autosmoothquant_b200 import harness
+
+    ids = torch.randint(0, harness.TINY.vocab, (2, 96), generator=torch.Generator().manual_seed(4)).to(DEV)
+    for qc in ({}, {"out": "per-token", "fc2": "per-token"}):
+        model = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=5, fuse_projections=True, glue=True)
+        monkeypatch.setenv("ASQ_NORM_PROLOGUE", "0")
+        want = model(ids, last_token_only=False)
+        monkeypatch.setenv("ASQ_NORM_PROLOGUE", "1")
+        before = L.launch_count()
+        got = model(ids, last_token_only=False)
+        assert L.launch_count() - before == 4 * len(model.layers) + 1  # four GEMM launches per layer + the final norm
+        assert torch.equal(got, want)
+
+
 def test_glue_stack_residual_epilogue_is_bit_identical(monkeypatch):
     from autosmoothquant_b200 import harness
 
