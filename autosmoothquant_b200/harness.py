@@ -275,11 +275,17 @@ def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Opt
     # o_proj: the module quantises the attention output in-kernel; under tensor parallelism it is the
     # row-parallel wrapper, whose forward ends with the all-reduce
     attn2 = attn.transpose(1, 2).reshape(B * S, nq * hd)
-    if os.environ.get("ASQ_OPROJ_SPLIT") == "1" and getattr(layer, "tp_world", 1) == 1:
+    if os.environ.get("ASQ_OPROJ_SPLIT") == "1" and getattr(layer, "tp_world", 1) == 1 and layer.o_proj.act_quant == "per-tensor":
+        # experiment: stand-alone quantisation kernel + int8-in GEMM instead of the in-kernel prologue
         om = layer.o_proj
         q8o, _ = _lib.quantize_act(attn2, _lib.ACT_SCALE, float(om.quant_scale.item()))
-        o = _lib.w8a8_linear_q8(q8o, om.weight, om.bias if om.use_bias else None, float(om.dequant_scale.item()),
-                                out_dtype=x2.dtype)
+        if fuse_res:
+            x2 = _lib.w8a8_linear_q8(q8o, om.weight, om.bias if om.use_bias else None, float(om.dequant_scale.item()),
+                                     out_dtype=x2.dtype, residual=x2)
+            o = None
+        else:
+            o = _lib.w8a8_linear_q8(q8o, om.weight, om.bias if om.use_bias else None, float(om.dequant_scale.item()),
+                                    out_dtype=x2.dtype)
     elif fuse_res:
         # residual add in o_proj's epilogue: x2 <- T(x2 + o_proj(attn)); the norm kernel then reads one tensor
         om = layer.o_proj
