@@ -1,0 +1,57 @@
+"""CPU checks of the host-side layouts and helpers the fused kernels rely on (no GPU, no library call)."""
+import torch
+
+from autosmoothquant_b200 import _lib as L
+from autosmoothquant_b200 import harness, moe
+
+
+def test_interleave_gate_up_layout():
+    """include/asq.h (asq_w8a8_gateup_swiglu_q8): rows [64b, 64b+32) = gate rows [32b, 32b+32), the next 32 = up rows."""
+    I, K = 96, 8
+    gate = torch.arange(I * K, dtype=torch.int32).view(I, K)
+    up = -gate - 1
+    il = L.interleave_gate_up(gate, up)
+    assert il.shape == (2 * I, K)
+    for b in range(I // 32):
+        assert torch.equal(il[64 * b:64 * b + 32], gate[32 * b:32 * b + 32])
+        assert torch.equal(il[64 * b + 32:64 * b + 64], up[32 * b:32 * b + 32])
+    v = L.interleave_gate_up(torch.arange(I), torch.arange(I) + 1000)  # vectors (scales, biases) use the same order
+    assert v[:32].tolist() == list(range(32)) and v[32:64].tolist() == list(range(1000, 1032))
+
+
+def test_rope_tables_blocked_index_formula():
+    """Entry (pos, col) of the [S, head_dim] table lives at ((col // 8) * S + pos) * 8 + col % 8."""
+    S, hd = 37, 128
+    table = torch.arange(S * hd, dtype=torch.float32).view(S, hd)
+    flat = L.rope_tables_blocked(table).reshape(-1)
+    for pos, col in ((0, 0), (5, 7), (36, 127), (11, 64), (20, 9)):
+        assert flat[((col // 8) * S + pos) * 8 + col % 8] == table[pos, col]
+
+
+def test_route_tokens_layout_cpu():
+    g = torch.Generator().manual_seed(0)
+    E, T, k = 8, 333, 2
+    sel = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)])
+    sel = torch.where(sel == 3, torch.full_like(sel, 4), sel)  # expert 3 gets no tokens
+    dest, blk, m_pad = moe.route_tokens(sel, E)
+    flat = sel.reshape(-1)
+    assert m_pad % 256 == 0 and blk.numel() == m_pad // 128 and blk.dtype == torch.int32
+    assert dest.unique().numel() == dest.numel() and int(dest.max()) < m_pad
+    assert torch.equal(blk[dest // 128].long(), flat)
+    counts = torch.bincount(flat, minlength=E)
+    used = int(((counts + 255) // 256 * 256).sum())
+    assert (blk[used // 128:] == -1).all() and (blk[:used // 128] >= 0).all() and not (blk == 3).any()
+    starts = torch.cumsum((counts + 255) // 256 * 256, 0) - (counts + 255) // 256 * 256
+    assert all(int(s) % 256 == 0 for s in starts)
+
+
+def test_quant_config_normalisation():
+    qc = harness.normalise_quant_config({"type": "fp8"})
+    assert qc["type"] == "fp8_e4m3" and qc["activation_scheme"] == "dynamic"
+    assert harness.normalise_quant_config({})["qkv"] == "per-tensor"
+    for bad in ({"type": "int4"}, {"qkv": "per-channel"}):
+        try:
+            harness.normalise_quant_config(bad)
+        except ValueError:
+            continue
+        raise AssertionError(f"{bad} accepted")
