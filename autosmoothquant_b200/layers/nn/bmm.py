@@ -1,50 +1,66 @@
-"""INT8 batched matmul modules with the reference's interface (autosmoothquant/layers/nn/bmm.py:1-70),
-backed by ``asq_i8bmm`` (tcgen05, one launch for the whole batch when M is a multiple of the tile height)."""
+"""INT8 batched-matmul modules, interface-compatible with the reference's ``layers/nn/bmm.py`` (three classes,
+``forward(a, b)`` with a [B, M, K] and b [B, N, K] int8, ``from_scale`` constructors, an ``a`` buffer holding alpha).
+
+All three share one implementation: ``asq_i8bmm`` (include/asq.h) computes the batch on the grouped tcgen05 path and
+only the epilogue differs — raw int32, alpha-scaled float32, or alpha-scaled, rounded and saturated int8
+(csrc/kernels/bmm.cu:10-211 in the reference).
+"""
+from __future__ import annotations
+
 import torch
+from torch import nn
 
-from ..._CUDA import bmm_s8t_s8n_f32t, bmm_s8t_s8n_s8t, bmm_s8t_s8n_s32t
-
-
-def _as_tensor(alpha):
-    return alpha if torch.is_tensor(alpha) else torch.tensor(alpha)
+from ... import _lib
 
 
-class BMM_S8T_S8N_S8T(torch.nn.Module):
-    def __init__(self, alpha):
+class _Int8BatchedMatmul(nn.Module):
+    """c[b] = epilogue(alpha * a[b] @ b[b]^T); subclasses fix the output type."""
+
+    OUT_DTYPE: torch.dtype = torch.int32
+    HAS_ALPHA = True
+
+    def __init__(self, alpha: float = 1.0):
         super().__init__()
-        self.register_buffer("a", torch.tensor(alpha))
+        if self.HAS_ALPHA:
+            self.register_buffer("a", torch.as_tensor(alpha))
+
+    def _alpha(self) -> float:
+        return float(self.a) if self.HAS_ALPHA else 1.0
+
+    def _set_alpha(self, value) -> "_Int8BatchedMatmul":
+        self.a = value if torch.is_tensor(value) else torch.as_tensor(value)
+        return self
 
     @torch.no_grad()
-    def forward(self, a, b):
-        # a: [B, M, K] int8, b: [B, N, K] int8 -> [B, M, N] int8
-        return bmm_s8t_s8n_s8t(a, b, self.a.item())
-
-    @staticmethod
-    def from_scale(a_scale, b_scale, output_scale):
-        mod = BMM_S8T_S8N_S8T(1.0)
-        mod.a = _as_tensor(a_scale * b_scale / output_scale)
-        return mod
+    def forward(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return _lib.i8bmm(a, b, self.OUT_DTYPE, self._alpha())
 
 
-class BMM_S8T_S8N_F32T(torch.nn.Module):
-    def __init__(self, alpha):
+class BMM_S8T_S8N_S8T(_Int8BatchedMatmul):
+    """int8 out: sat_i8(rint(alpha * acc)), alpha = a_scale * b_scale / output_scale."""
+
+    OUT_DTYPE = torch.int8
+
+    @classmethod
+    def from_scale(cls, a_scale, b_scale, output_scale):
+        return cls(1.0)._set_alpha(a_scale * b_scale / output_scale)
+
+
+class BMM_S8T_S8N_F32T(_Int8BatchedMatmul):
+    """float32 out: alpha * acc, alpha = a_scale * b_scale."""
+
+    OUT_DTYPE = torch.float32
+
+    @classmethod
+    def from_scale(cls, a_scale, b_scale):
+        return cls(1.0)._set_alpha(a_scale * b_scale)
+
+
+class BMM_S8T_S8N_S32T(_Int8BatchedMatmul):
+    """int32 out: the exact accumulators; no scale."""
+
+    OUT_DTYPE = torch.int32
+    HAS_ALPHA = False
+
+    def __init__(self):
         super().__init__()
-        self.register_buffer("a", torch.tensor(alpha))
-
-    @torch.no_grad()
-    def forward(self, a, b):
-        # a: [B, M, K] int8, b: [B, N, K] int8 -> [B, M, N] float32
-        return bmm_s8t_s8n_f32t(a, b, self.a.item())
-
-    @staticmethod
-    def from_scale(a_scale, b_scale):
-        mod = BMM_S8T_S8N_F32T(1.0)
-        mod.a = _as_tensor(a_scale * b_scale)
-        return mod
-
-
-class BMM_S8T_S8N_S32T(torch.nn.Module):
-    @torch.no_grad()
-    def forward(self, a, b):
-        # a: [B, M, K] int8, b: [B, N, K] int8 -> [B, M, N] int32
-        return bmm_s8t_s8n_s32t(a, b)
