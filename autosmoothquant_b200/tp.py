@@ -97,6 +97,17 @@ class CudaBackend:
         return s
 
     @staticmethod
+    def fp8_local_row_scales(x2):
+        _, s = _lib.quantize_act(x2, _lib.ACT_PER_TOKEN, fp8=True)
+        return s
+
+    @staticmethod
+    def fp8_linear_given_scales(module, x2, row_scale, out_fp32):
+        return _lib.fp8_linear(x2, module.weight, module._bias_f32(), _lib.ACT_ROW_SCALE_GIVEN, 1.0,
+                               float(module.weight_scale.item()), out_dtype=torch.float32 if out_fp32 else None,
+                               row_scale_out=row_scale)
+
+    @staticmethod
     def int32_partial(module, x2, mode, quant_scale, row_scale=None):
         if mode == _lib.ACT_PER_TOKEN:
             raise NotImplementedError("int32 reduction needs global row scales (local_scales=False)")
@@ -119,6 +130,8 @@ class ColumnParallelLinear(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.shard
         if isinstance(m, FP8LinearDynamic):  # replicated input: the module's own fused launch, output stays sharded
+            if hasattr(self.backend, "fp8_module_forward"):
+                return self.backend.fp8_module_forward(m, x)
             return m(x)
         x2 = x.reshape(-1, m.in_features)
         if m.act_quant == "per-token":
@@ -219,11 +232,10 @@ def _rowparallel_forward_fp8(self, m: FP8LinearDynamic, x: torch.Tensor, x2: tor
     products are rounded to the activation dtype (or kept fp32, reduce="fp32") and summed by one all-reduce."""
     if m.act_quant != "per-token" or self.reduce in ("int32", "fused"):
         raise NotImplementedError("FP8 row-parallel: per-token activations with reduce='native' or 'fp32' only")
-    _, row_scale = _lib.quantize_act(x2, _lib.ACT_PER_TOKEN, fp8=True)
+    row_scale = self.backend.fp8_local_row_scales(x2)
     if not self.local_scales:
         dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)
-    y = _lib.fp8_linear(x2, m.weight, m._bias_f32(), _lib.ACT_ROW_SCALE_GIVEN, 1.0, float(m.weight_scale.item()),
-                        out_dtype=torch.float32 if self.reduce == "fp32" else None, row_scale_out=row_scale)
+    y = self.backend.fp8_linear_given_scales(m, x2, row_scale, self.reduce == "fp32")
     dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
     return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
 

@@ -51,6 +51,32 @@ class OracleBackend:
     def int32_partial(cls, module, x2, mode, quant_scale, row_scale=None):
         return torch.from_numpy(O.int8_gemm_i32(cls._quant(x2, mode, quant_scale, row_scale), module.weight.numpy()))
 
+    # ---- FP8-e4m3 per-token (BASELINE config 5), fp32 activations as the reference effectively runs it
+    @staticmethod
+    def _w_bytes(module):
+        return module.weight.view(torch.uint8).numpy()
+
+    @classmethod
+    def fp8_local_row_scales(cls, x2):
+        return torch.from_numpy(O.quantize_act_fp8(x2.float().numpy(), "f32", "per-token")[1])
+
+    @classmethod
+    def fp8_linear_given_scales(cls, module, x2, row_scale, out_fp32):
+        x = x2.float().numpy()
+        s = row_scale.numpy().reshape(-1, 1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q = O.e4m3_encode(np.clip(x / s, -448.0, 448.0))
+        y = O.fp8_linear_exact(q, cls._w_bytes(module), s.reshape(-1), float(module.weight_scale),
+                               module.bias.numpy() if module.use_bias else None)
+        return torch.from_numpy(y.astype(np.float32))
+
+    @classmethod
+    def fp8_module_forward(cls, module, x):
+        x2 = x.reshape(-1, module.in_features).float().numpy()
+        q, s = O.quantize_act_fp8(x2, "f32", "per-token")
+        y = O.fp8_linear_exact(q, cls._w_bytes(module), s, float(module.weight_scale), module.bias.numpy() if module.use_bias else None)
+        return torch.from_numpy(y.astype(np.float32)).view(*x.shape[:-1], module.out_features)
+
 
 def _free_port():
     with socket.socket() as s:
@@ -111,6 +137,47 @@ def test_tp2_matches_unsharded_oracle(act_quant):
         assert ok_col, f"rank {rank}: column-parallel shard differs"
         assert ok_row, f"rank {rank}: int32 row-parallel result differs from the unsharded oracle"
         assert ok_native, f"rank {rank}: fp32-reduced row-parallel result out of tolerance"
+
+
+def _worker_fp8(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from autosmoothquant_b200 import tp
+        from autosmoothquant_b200.layers.nn.linear import FP8LinearDynamic
+
+        torch.manual_seed(0)
+        K, I = 64, 96
+        f1 = FP8LinearDynamic.from_float(torch.nn.Linear(K, I, bias=False), act_quant="per-token")
+        f2 = FP8LinearDynamic.from_float(torch.nn.Linear(I, K, bias=True), act_quant="per-token")
+        x = torch.randn(5, 4, K)
+        col = tp.ColumnParallelLinear(tp.shard_column(f1, rank, world), backend=OracleBackend)
+        row = tp.RowParallelLinear(tp.shard_row(f2, rank, world), reduce="fp32", backend=OracleBackend, has_bias=True)
+        h_local = col(x)
+        y = row(h_local)
+        h_full = OracleBackend.fp8_module_forward(f1, x)
+        lo, hi = rank * I // world, (rank + 1) * I // world
+        ok_col = bool(torch.equal(h_local, h_full[..., lo:hi]))
+        y_full = OracleBackend.fp8_module_forward(f2, h_full)
+        # the global per-token scale (max-all-reduced) makes every rank quantise exactly as the unsharded module does;
+        # only the fp32 summation of the two K halves differs from the fp64 evaluation of the whole K
+        ok_row = bool(torch.allclose(y, y_full, rtol=1e-5, atol=1e-5 * float(y_full.abs().max())))
+        ret[rank] = (ok_col, ok_row, tuple(tp.shard_row(f2, rank, world).weight.shape), tp.shard_row(f2, rank, world).use_bias)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp2_fp8_per_token_matches_unsharded_oracle():
+    """BASELINE config 5 plumbing (FP8-e4m3 per-token, column- then row-parallel) on CPU over gloo."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_fp8, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        ok_col, ok_row, shape, has_bias = ret[rank]
+        assert ok_col and ok_row, f"rank {rank}: col {ok_col} row {ok_row}"
+        assert shape == (64, 48) and has_bias == (rank == 0)  # K sharded, bias only on rank 0
 
 
 def test_row_parallel_int32_identity():
