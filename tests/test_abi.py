@@ -71,3 +71,24 @@ def test_fails_loudly_without_a_device(lib):
     rc = lib.asq_i8gemm_o32(addr, addr, addr, 16, 16, 16, None, 0, None)
     assert rc == -3  # ASQ_ERR_CUDA: no fallback
     assert lib.asq_device_supported() == 0
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/asq.h must be consumable from C (the cgo / JNI / ctypes side of the boundary): compile a C99
+    translation unit against it with -pedantic and link it with the shared library."""
+    import shutil
+    import subprocess
+
+    from autosmoothquant_b200 import _lib as L
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = L.LIB_PATH.parent.parent
+    src = tmp_path / "t.c"
+    src.write_text('#include "asq.h"\n#include <stdio.h>\nint main(void){ printf("%d %zu\\n", asq_version(), '
+                   'asq_workspace_bytes(0, 0)); return asq_version() == ASQ_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root / 'include'}", str(src), "-o", str(exe),
+                    str(L.LIB_PATH), f"-Wl,-rpath,{L.LIB_PATH.parent}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == L.load().asq_version() and int(out[1]) == L.load().asq_workspace_bytes(0, 0)
