@@ -27,7 +27,7 @@ int asq_glue_fail(int code, const char* fmt, ...);  // defined in asq_kernels.cu
 namespace asq_smallm {
 
 constexpr int COLS_PER_CTA = 16;  // two 8-column mma tiles per CTA
-constexpr int UNROLL = 4;         // 64-byte K steps of W in flight per lane
+constexpr int UNROLL = 8;         // 64-byte K steps of W in flight per lane (128 bytes per lane, 4 KB per warp)
 
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 v;
