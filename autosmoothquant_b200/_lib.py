@@ -54,6 +54,7 @@ EXPORTED_SYMBOLS = (
     "asq_i8bmm",
     "asq_ar_buffer_bytes",
     "asq_w8a8_linear_q8_allreduce",
+    "asq_q8_linear_allreduce_nvls",
     "asq_dev_alloc",
     "asq_dev_free",
     "asq_ipc_export",
@@ -156,6 +157,9 @@ def load():
         lib.asq_w8a8_linear_q8_allreduce.restype = c_i
         lib.asq_w8a8_linear_q8_allreduce.argtypes = [c_vp, c_vp, c_vp, c_vp, c_pp, c_i, c_i64, c_i64, c_i64, c_f, c_vp,
                                                      c_pp, c_pp, c_i, c_i, c_i, c_vp, c_vp]
+        lib.asq_q8_linear_allreduce_nvls.restype = c_i
+        lib.asq_q8_linear_allreduce_nvls.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f,
+                                                     c_vp, c_pp, c_i, c_i, c_vp]
         lib.asq_dev_alloc.restype = c_i
         lib.asq_dev_alloc.argtypes = [c_sz, c_pp]
         lib.asq_dev_free.restype = c_i
@@ -675,12 +679,17 @@ def w8a8_grouped_linear(
     group_dequant_scale_up: Optional[torch.Tensor] = None,
     swiglu: bool = False,
     div_mode: Optional[int] = None,
+    row_scale: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """All experts of an MoE block in one launch (include/asq.h: asq_w8a8_grouped_linear).  x [M_pad, K] holds the
     routed rows sorted by expert, every expert's segment padded to a multiple of 256 rows; group_of_blk (int32
-    [M_pad / 128]) names the expert of each 128-row block (-1: unused); weight_stacked [G * N, K]."""
+    [M_pad / 128]) names the expert of each 128-row block (-1: unused); weight_stacked [G * N, K].
+    act_mode ACT_ROW_SCALE_GIVEN quantises with the caller's row_scale [M_pad] fp32 (tensor-parallel w2)."""
     global _launches
-    dev = _require_cuda(x, weight_stacked, group_of_blk, group_dequant_scale, group_quant_scale, group_dequant_scale_up)
+    dev = _require_cuda(x, weight_stacked, group_of_blk, group_dequant_scale, group_quant_scale, group_dequant_scale_up, row_scale)
+    if act_mode == ACT_ROW_SCALE_GIVEN and (row_scale is None or row_scale.dtype != torch.float32 or row_scale.numel() != x.shape[0]
+                                            or not row_scale.is_contiguous()):
+        raise ValueError("ACT_ROW_SCALE_GIVEN needs row_scale: contiguous float32 [M_pad]")
     G = group_dequant_scale.numel()
     if x.dim() != 2 or weight_stacked.dtype != torch.int8 or weight_stacked.shape[1] != x.shape[1] or weight_stacked.shape[0] % G:
         raise ValueError("w8a8_grouped_linear expects x [M_pad,K] and stacked int8 weights [G*N,K]")
@@ -701,7 +710,8 @@ def w8a8_grouped_linear(
         rc = lib.asq_w8a8_grouped_linear(
             x.data_ptr(), _code(x.dtype), weight_stacked.data_ptr(), y.data_ptr(), _code(out_dtype), M, N, K, G,
             group_of_blk.data_ptr(), group_dequant_scale.data_ptr(), _ptr(group_dequant_scale_up), _ptr(group_quant_scale),
-            act_mode, None, 1 if swiglu else 0, _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream)
+            act_mode, _ptr(row_scale) if act_mode == ACT_ROW_SCALE_GIVEN else None, 1 if swiglu else 0,
+            _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream)
     _check(rc)
     _launches += 1
     return y

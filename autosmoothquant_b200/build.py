@@ -40,7 +40,7 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > built for p in SOURCES + HEADERS)
 
 
-N_KERNEL_TUS = 22  # asq_kernels.cu is compiled once per kernel instantiation set (-DASQ_TU=1..22) + once for the host side (0)
+N_KERNEL_TUS = 24  # asq_kernels.cu is compiled once per kernel instantiation set (-DASQ_TU=1..24) + once for the host side (0)
 OBJ_DIR = Path(os.environ.get("ASQ_OBJ_DIR", "/tmp/asq_b200_obj" + ("_" + os.environ["ASQ_LIB_NAME"] if "ASQ_LIB_NAME" in os.environ else "")))  # objects stay out of the tree
 
 

@@ -133,6 +133,14 @@ struct LinearParams {
                        // reaches every rank through the switch) instead of one TMA store per rank
   uint32_t* ar_ctl[8];
   uint32_t* ar_recv[8];
+  // In-switch all-reduce (F_NVLS): every rank TMA-stores its 16-bit partial tiles into its OWN symmetric buffer (p.y)
+  // and bumps a counter on the tile's owner (rank tile % world, ar_ctl[owner]); the owner's epilogue warps then sum
+  // the world copies of their part of the tile with multimem.ld_reduce on the buffers' multicast address (the
+  // NVSwitch adds them, fp32 accumulation) and multimem.st the sums into every rank's output.  All ranks walk the
+  // tiles in the SAME order, so a tile's partials complete at about the same time everywhere and the reduction of
+  // tile i overlaps the main loop of tile i+1.
+  const uint8_t* nvls_p_mc;  // multicast address of the partial buffers [M, N] 16-bit (NULL: not an NVLS launch)
+  uint8_t* nvls_y_mc;        // multicast address of the outputs [M, N] 16-bit
   int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
   unsigned long long* dbg;  // optional timeline buffer (8 slots per CTA), nullptr in production
 };
@@ -873,6 +881,7 @@ enum Feat : int {
   F_OUT_ANY = 64,  // 4-byte staged outputs, raw int32, alpha/beta, direct (unstaged) stores
   F_PHASE1 = 128,  // fused activation-quantisation prologue
   F_RESID = 256,   // residual add in the 16-bit epilogue: y = T(residual + T(dequantised result))
+  F_NVLS = 512,    // in-switch all-reduce of the 16-bit partial tiles (multimem.ld_reduce / multimem.st)
   F_FULL = F_SK | F_GROUP | F_SWIGLU | F_ROPE | F_DEQ16 | F_OUT_ANY | F_PHASE1 | F_RESID,
 };
 
@@ -910,6 +919,7 @@ struct TileWalk {
       sg.ar_tile = t;
       sg.role = (owner == p.ar_rank) ? SEG_AR_OWNER : SEG_AR_CONTRIB;
     }
+    if ((FEAT & F_NVLS) != 0) sg.ar_tile = t;  // same walk order on every rank; owner = t % world
     tile_coords(t, p, sg.m_blk, n_blk);
     sg.group = 0;
     if ((FEAT & F_GROUP) != 0)
@@ -982,6 +992,70 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void red_release_sys_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- in-switch reduction (NVLS).  One 16-byte multimem.ld_reduce returns the SUM over all ranks' copies of eight
+// 16-bit values (the switch adds them with fp32 accumulation); multimem.st writes 16 bytes into every rank's copy.
+template <bool BF>
+__device__ __forceinline__ uint4 multimem_ld_reduce_16(const void* mc_addr) {
+  uint4 v;
+  if (BF) asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_addr) : "memory");
+  else    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_addr) : "memory");
+  return v;
+}
+template <bool BF>
+__device__ __forceinline__ void multimem_st_16(void* mc_addr, const uint4& v) {
+  if (BF) asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  else    asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One epilogue warp's part of an owned tile, remembered until its partials have arrived from every rank.
+struct NvlsPending {
+  int valid, row0, col0, ngroups, half;
+  uint32_t* counter;
+};
+
+// Sum this warp's part (32 rows x its 64-column groups) of an owned tile over all ranks and broadcast it.
+// `blocking` == false: return false at once if some rank's partial has not landed yet.
+template <bool BF>
+__device__ __forceinline__ bool nvls_reduce_part(const LinearParams& p, NvlsPending& pd, int lane, bool blocking) {
+  uint32_t seen = 0;
+  if (lane == 0) {
+    const uint32_t want = static_cast<uint32_t>(p.ar_world);
+    seen = ld_acquire_sys(pd.counter);
+    while (blocking && seen != want) { __nanosleep(64); seen = ld_acquire_sys(pd.counter); }
+    seen = (seen == want) ? 1u : 0u;
+  }
+  seen = __shfl_sync(0xffffffffu, seen, 0);
+  if (!seen) return false;
+  fence_acq_rel_sys();
+  const int N = p.N;
+#pragma unroll 1
+  for (int g = pd.half; g < pd.ngroups; g += 2) {
+    const int col = pd.col0 + g * UNIT_N + (lane & 7) * 8;  // this lane's 16-byte piece of a 128-byte row segment
+    uint4 v[8];
+    bool ok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = pd.row0 + i * 4 + (lane >> 3);
+      ok[i] = row < p.M && col < N;
+      if (ok[i]) v[i] = multimem_ld_reduce_16<BF>(p.nvls_p_mc + (static_cast<size_t>(row) * N + col) * 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = pd.row0 + i * 4 + (lane >> 3);
+      if (ok[i]) multimem_st_16<BF>(p.nvls_y_mc + (static_cast<size_t>(row) * N + col) * 2, v[i]);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *pd.counter = 0u;  // re-arm: the peers' next increments come after this launch's end handshake
+  pd.valid = 0;
+  return true;
+}
 
 // Output maps of the other ranks' y buffers (all-reduce mode), in rank order skipping self.  Only the AR
 // instantiations of the kernel carry them: 896 bytes of launch parameters cost ~2 us per launch (measured).
@@ -1014,6 +1088,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr bool kROPE = (FEAT & F_ROPE) != 0, kDEQ16 = (FEAT & F_DEQ16) != 0, kOUT_ANY = (FEAT & F_OUT_ANY) != 0;
   constexpr bool kLoop = (FEAT & (F_DEQ16 | F_OUT_ANY | F_SK | F_AR)) != 0;  // the generic per-group epilogue loop
   constexpr bool kRESID = (FEAT & F_RESID) != 0;
+  constexpr bool kNVLS = (FEAT & F_NVLS) != 0;
   using Cfg = TileCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -1218,6 +1293,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                (p.epi_kind == EPI_DEQUANT || p.epi_kind == EPI_SWIGLU);
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     uint32_t resid_phase = 0;  // parity of this warp's residual-tile barrier
+    NvlsPending nvls_pend;     // F_NVLS: this warp's part of the last owned tile, not yet reduced
+    nvls_pend.valid = 0;
     // all-reduce mode: this launch's epoch = 1 + the epoch of the last launch that finished on this rank
     const uint32_t ar_epoch = (AR && p.ar_world > 1) ? __ldcg(p.ar_ctl[p.ar_rank]) + 1u : 0u;
     int it = 0;
@@ -1613,6 +1690,35 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kSK && sg.role == SEG_OWNER)
           for (int c = 0; c < n_contrib; ++c) *sk_flag(p, worker + 1 + c, CG, cta_rank, ew) = 0u;  // consumed: re-arm
       }
+      if constexpr (kNVLS) {
+        // This warp's part of the tile's partial is on its way into this rank's buffer: once it has LANDED (bulk
+        // stores complete, not merely read from shared memory) tell the tile's owner.  The accumulator was already
+        // handed back above, so the next tile's MMAs run while this warp waits and reduces.
+        const int owner = sg.ar_tile % p.ar_world;
+        uint32_t* ctr = p.ar_ctl[owner] + AR_FLAG_BASE +
+                        (static_cast<size_t>(sg.ar_tile / p.ar_world) * CG + cta_rank) * NUM_EPI_WARPS + ew;
+        if (lane == 0) {
+          tma_store_wait_all();
+          fence_proxy_async_all();  // async-proxy (TMA) writes before the generic-proxy release below
+          fence_acq_rel_sys();
+          red_release_sys_add(ctr, 1u);
+        }
+        __syncwarp();
+        const bool bf = (p.y_dtype == ASQ_BF16);
+        if (owner == p.ar_rank) {
+          // an owned tile: first finish the previous one (its partials had a whole tile time to arrive), then queue this one
+          if (nvls_pend.valid) { if (bf) nvls_reduce_part<true>(p, nvls_pend, lane, true); else nvls_reduce_part<false>(p, nvls_pend, lane, true); }
+          nvls_pend.valid = 1; nvls_pend.row0 = row0; nvls_pend.col0 = tile_col0; nvls_pend.ngroups = ngroups;
+          nvls_pend.half = half; nvls_pend.counter = ctr;
+        } else if (nvls_pend.valid) {
+          if (bf) nvls_reduce_part<true>(p, nvls_pend, lane, false); else nvls_reduce_part<false>(p, nvls_pend, lane, false);
+        }
+      }
+    }
+    if constexpr (kNVLS) {
+      if (nvls_pend.valid) {
+        if (p.y_dtype == ASQ_BF16) nvls_reduce_part<true>(p, nvls_pend, lane, true); else nvls_reduce_part<false>(p, nvls_pend, lane, true);
+      }
     }
     if (lane == 0) tma_store_wait_all();  // staged tiles fully written before the CTA retires
     if (ew == 0 && lane == 0) ASQ_STAMP(6);
@@ -1625,7 +1731,7 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (threadIdx.x == 0) ASQ_STAMP(7);
-  if (AR && p.ar_world > 1 && threadIdx.x == 0) {
+  if ((AR || kNVLS) && p.ar_world > 1 && threadIdx.x == 0) {
     // This CTA's tiles are stored everywhere (each epilogue warp waited for its TMA stores before the sync above).
     // The last CTA of the rank tells every peer "rank r finished launch e", waits for the same word from every
     // peer (their stores into OUR y and their reads of OUR partials are then complete) and advances the epoch.
@@ -1916,6 +2022,7 @@ int max_multicast_clusters(int dev) {
 #define ASQ_LEAN_PHASE1_RESID (asq::F_DEQ16 | asq::F_PHASE1 | asq::F_RESID)
 #define ASQ_LEAN_PHASE1_ROPE (asq::F_ROPE | asq::F_PHASE1)
 #define ASQ_LEAN_PHASE1_SWIGLU (asq::F_SWIGLU | asq::F_PHASE1)
+#define ASQ_LEAN_NVLS (asq::F_NVLS | asq::F_DEQ16)
 #if ASQ_TU == 0 || ASQ_TU == 1
 ASQ_LAUNCH_INST(false, 1, 1, asq::F_FULL)
 #endif
@@ -1977,6 +2084,14 @@ ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_ROPE)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 22
 ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_PHASE1_SWIGLU)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 23
+ASQ_LAUNCH_INST(false, 2, 1, ASQ_LEAN_NVLS)
+ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_NVLS)
+#endif
+#if ASQ_TU == 0 || ASQ_TU == 24
+ASQ_LAUNCH_INST(true, 2, 1, ASQ_LEAN_NVLS)
+ASQ_LAUNCH_INST(true, 1, 1, ASQ_LEAN_NVLS)
 #endif
 #if ASQ_TU == 0 || ASQ_TU == 19
 ASQ_LAUNCH_INST(false, 1, 1, ASQ_LEAN_PLAIN)
@@ -2170,6 +2285,17 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     if (!out16r || !p.tma_store || p.epi_kind != asq::EPI_DEQUANT || p.rope_cos != nullptr || p.ar_world > 1 || p.N % 8 != 0 ||
         (reinterpret_cast<uintptr_t>(p.residual) & 15))
       return fail(ASQ_ERR_INVALID, "residual add needs a 16-bit dequantised output with N %% 8 == 0 and a 16-byte aligned residual");
+  }
+  if (p.nvls_p_mc != nullptr) {
+    // in-switch all-reduce: the ordinary 16-bit staged epilogue writes the partial tiles, the owners reduce them
+    const bool out16n = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
+    if (!p.tma_store || !out16n || p.epi_kind != asq::EPI_DEQUANT || p.x != nullptr || p.sk_enabled || mc != 1)
+      return fail(ASQ_ERR_INVALID, "nvls all-reduce needs 8-bit activations and a 16-byte aligned 16-bit output row pitch");
+    const asq::ExtraMapsT<0> none_nvls{};
+    if (cg == 2) return fp8 ? launch_cfg<true, 2, 1, ASQ_LEAN_NVLS>(tmA, tmB, tmBu, tmY, none_nvls, p, workers, stream)
+                            : launch_cfg<false, 2, 1, ASQ_LEAN_NVLS>(tmA, tmB, tmBu, tmY, none_nvls, p, workers, stream);
+    return fp8 ? launch_cfg<true, 1, 1, ASQ_LEAN_NVLS>(tmA, tmB, tmBu, tmY, none_nvls, p, workers, stream)
+               : launch_cfg<false, 1, 1, ASQ_LEAN_NVLS>(tmA, tmB, tmBu, tmY, none_nvls, p, workers, stream);
   }
   if (p.ar_world > 1) {
     if (!p.tma_store || peer_y == nullptr) return fail(ASQ_ERR_INVALID, "all-reduce mode needs a 16-byte aligned 16-bit output row pitch");
@@ -2595,8 +2721,10 @@ int asq_w8a8_grouped_linear(const void* x, int x_dtype, const int8_t* w_stacked,
   if (num_groups < 1 || num_groups > 4096 || group_of_blk == nullptr || group_dequant_scale == nullptr)
     return fail(ASQ_ERR_INVALID, "grouped: need 1..4096 groups, the block->group table and the per-group dequant scales");
   if (M_pad % asq::BLOCK_M != 0) return fail(ASQ_ERR_INVALID, "grouped: M_pad=%lld must be a multiple of 128 (segments padded to 256 rows)", (long long)M_pad);
-  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN)
-    return fail(ASQ_ERR_INVALID, "grouped: act_mode must be ROUND, SCALE or PER_TOKEN");
+  if (act_mode != ASQ_ACT_ROUND && act_mode != ASQ_ACT_SCALE && act_mode != ASQ_ACT_PER_TOKEN && act_mode != ASQ_ACT_ROW_SCALE_GIVEN)
+    return fail(ASQ_ERR_INVALID, "grouped: act_mode must be ROUND, SCALE, PER_TOKEN or ROW_SCALE_GIVEN");
+  if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN && row_scale_out == nullptr && M_pad > 0)
+    return fail(ASQ_ERR_INVALID, "grouped: ASQ_ACT_ROW_SCALE_GIVEN needs the [M_pad] row scales in row_scale");
   if (act_mode == ASQ_ACT_SCALE && group_quant_scale == nullptr) return fail(ASQ_ERR_INVALID, "grouped: ASQ_ACT_SCALE needs group_quant_scale");
   if (div_mode != ASQ_DIV_RECIPROCAL && div_mode != ASQ_DIV_EXACT) return fail(ASQ_ERR_INVALID, "bad div_mode %d", div_mode);
   if (swiglu) {
@@ -2616,7 +2744,8 @@ int asq_w8a8_grouped_linear(const void* x, int x_dtype, const int8_t* w_stacked,
   asq::LinearParams p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.a_q = ws.a_q; p.row_scale = ws.row_scale; p.sync = ws.sync;  // no stream-K in grouped launches
-  p.row_scale_out = row_scale_out;
+  if (act_mode == ASQ_ACT_ROW_SCALE_GIVEN) p.row_scale_in = row_scale_out;  // in: caller-supplied scales (tensor-parallel w2)
+  else p.row_scale_out = row_scale_out;
   p.quant_scale = 1.f; p.inv_quant_scale = 1.f; p.qmax = 127.0f; p.inv_qmax = 1.0f / 127.0f;
   p.y = y; p.dequant_scale = 1.f; p.dequant_scale_up = 1.f;
   p.M = static_cast<int>(M_pad); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
@@ -2677,6 +2806,36 @@ int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const
     if (r != rank) peers[n++] = y_all[r];
   }
   return launch_linear(false, xq, w, p, static_cast<cudaStream_t>(stream), peers);
+}
+
+int asq_q8_linear_allreduce_nvls(const void* xq, int fp8, const float* row_scale, const void* w, const float* bias,
+                                 void* partial_local, const void* partial_mc, void* y_mc, int y_dtype, int64_t M,
+                                 int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                                 void* const* ctl_all, int rank, int world, void* stream) {
+  if (world < 2 || world > 8 || rank < 0 || rank >= world || ctl_all == nullptr)
+    return fail(ASQ_ERR_INVALID, "nvls allreduce: bad rank %d / world %d or null control table", rank, world);
+  for (int r = 0; r < world; ++r)
+    if (ctl_all[r] == nullptr) return fail(ASQ_ERR_INVALID, "nvls allreduce: rank %d control buffer is null", r);
+  if (partial_local == nullptr || partial_mc == nullptr || y_mc == nullptr || (reinterpret_cast<uintptr_t>(partial_mc) & 15) ||
+      (reinterpret_cast<uintptr_t>(y_mc) & 15))
+    return fail(ASQ_ERR_INVALID, "nvls allreduce: the partial / output buffers must be non-null and 16-byte aligned");
+  int rc = check_common(xq, w, partial_local, M, N, K);
+  if (rc != ASQ_OK) return rc;
+  if (y_dtype != ASQ_BF16 && y_dtype != ASQ_F16) return fail(ASQ_ERR_INVALID, "nvls allreduce: y dtype must be f16 or bf16");
+  if (N % 8 != 0) return fail(ASQ_ERR_INVALID, "nvls allreduce: N=%lld must be a multiple of 8 (16-byte output rows)", (long long)N);
+  if (M == 0) return fail(ASQ_ERR_INVALID, "nvls allreduce: M must be positive (every rank has to launch)");
+  asq::LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = partial_local; p.bias = bias; p.col_scale = col_scale; p.dequant_scale = dequant_scale;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.y_dtype = y_dtype; p.epi_kind = asq::EPI_DEQUANT;
+  p.act_mode = row_scale != nullptr ? ASQ_ACT_ROW_SCALE_GIVEN : ASQ_ACT_ROUND;
+  p.row_scale = const_cast<float*>(row_scale);
+  p.ar_world = world; p.ar_rank = rank;
+  p.nvls_p_mc = static_cast<const uint8_t*>(partial_mc);
+  p.nvls_y_mc = static_cast<uint8_t*>(y_mc);
+  for (int r = 0; r < world; ++r) p.ar_ctl[r] = static_cast<uint32_t*>(ctl_all[r]);
+  return launch_linear(fp8 != 0, xq, w, p, static_cast<cudaStream_t>(stream));
 }
 
 // ---- device memory shared between the processes of one node (cudaMalloc + CUDA IPC), used for the buffers above

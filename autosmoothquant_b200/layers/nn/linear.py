@@ -303,18 +303,28 @@ class FP8LinearDynamic(_FP8Base):
         return y.view(*x.shape[:-1], self.out_features)
 
     @staticmethod
-    def from_float(module: nn.Linear, input_scale=1.0, save_device=torch.device("cpu"), act_quant="per-token"):
+    def from_float(module: nn.Linear, input_scale=1.0, save_device=torch.device("cpu"), act_quant="per-token",
+                   reference_compat: bool = True):
+        """reference_compat=True (default) reproduces the reference converter to the letter (:429-452): it passes
+        ``use_bias`` in the ``act_quant`` slot of the constructor, so the module it returns carries
+        ``act_quant in {True, False}`` — its forward takes the per-TENSOR dynamic branch — and ``use_bias=False`` — a
+        bias is stored (and saved) but never added.  Identical inputs therefore give identical results to a module
+        converted by the reference.  reference_compat=False builds what the assertion promises: a per-token module
+        that adds its bias (the form the reference's model constructors create when they LOAD a checkpoint,
+        models/llama.py:83-90)."""
         assert act_quant == "per-token"  # dynamic scale only supports per-token activation quant
         quant_weight, weight_scale = per_tensor_quantize_fp8(module.weight.data)
         use_bias = module.bias is not None
-        # NOTE: the reference passes `use_bias` in the act_quant slot here (:444-446), producing modules
-        # that take the per-tensor branch and drop the bias; this implementation builds what the
-        # assertion above promises.
-        out = FP8LinearDynamic(module.in_features, module.out_features, act_quant, use_bias)
+        if reference_compat:
+            out = FP8LinearDynamic(module.in_features, module.out_features, use_bias)  # sic: the act_quant slot
+            if use_bias:
+                out.register_buffer("bias", copy.deepcopy(module.bias.data).to(save_device))
+        else:
+            out = FP8LinearDynamic(module.in_features, module.out_features, act_quant, use_bias)
+            if use_bias:
+                out.bias = copy.deepcopy(module.bias.data).to(torch.float32).to(save_device)
         out.weight = quant_weight.to(save_device)
         out.weight_scale = (input_scale * weight_scale).to(torch.float32).cpu()
-        if use_bias:
-            out.bias = copy.deepcopy(module.bias.data).to(torch.float32).to(save_device)
         return out
 
 

@@ -56,12 +56,25 @@ class GroupedInt8Experts(nn.Module):
         self.register_buffer("w2_quant_scale", torch.tensor([float(getattr(m, "quant_scale", 1.0)) for m in w2], **f32))  # per-tensor fc2 only
 
     @torch.no_grad()
-    def forward(self, x_sorted: torch.Tensor, group_of_blk: torch.Tensor) -> torch.Tensor:
-        """x_sorted [M_pad, hidden] (rows sorted by expert, segments padded to 256) -> [M_pad, hidden]."""
+    def forward(self, x_sorted: torch.Tensor, group_of_blk: torch.Tensor, tp_group=None, tp_world: int = 1,
+                local_scales: bool = False) -> torch.Tensor:
+        """x_sorted [M_pad, hidden] (rows sorted by expert, segments padded to 256) -> [M_pad, hidden].
+        tp_world > 1: this module holds the Megatron shard of every expert (w1 / w3 split by column, w2 by row) and
+        the result is this rank's PARTIAL sum over its ffn slice.  Per-token fc2 then needs the row absmax over the
+        whole ffn dimension (SURVEY 8(e) wrinkle): the local per-token scales are max-all-reduced and w2 quantises
+        with the supplied scales, which keeps the integer operands identical to the unsharded module
+        (local_scales=True skips the exchange: valid, not bit-identical)."""
         mode1 = _lib.ACT_PER_TOKEN if self.fc1_act == "per-token" else _lib.ACT_ROUND
         a = _lib.w8a8_grouped_linear(x_sorted, self.w13, group_of_blk, self.w1_scale, mode1,
                                      group_dequant_scale_up=self.w3_scale, swiglu=True)
         if self.fc2_act == "per-token":
+            if tp_world > 1 and not local_scales:
+                import torch.distributed as dist
+
+                _, row_scale = _lib.quantize_act(a, _lib.ACT_PER_TOKEN)
+                dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=tp_group)
+                return _lib.w8a8_grouped_linear(a, self.w2, group_of_blk, self.w2_scale, _lib.ACT_ROW_SCALE_GIVEN,
+                                                row_scale=row_scale)
             return _lib.w8a8_grouped_linear(a, self.w2, group_of_blk, self.w2_scale, _lib.ACT_PER_TOKEN)
         return _lib.w8a8_grouped_linear(a, self.w2, group_of_blk, self.w2_scale, _lib.ACT_SCALE,
                                         group_quant_scale=self.w2_quant_scale)
@@ -91,8 +104,10 @@ def route_tokens(selected_experts: torch.Tensor, num_experts: int):
 
 @torch.no_grad()
 def sparse_moe_forward(hidden_states: torch.Tensor, gate_weight: torch.Tensor, experts: GroupedInt8Experts,
-                       top_k: int = 2) -> torch.Tensor:
-    """HF 4.42 MixtralSparseMoeBlock.forward with the expert loop replaced by two grouped launches."""
+                       top_k: int = 2, tp_group=None, tp_world: int = 1) -> torch.Tensor:
+    """HF 4.42 MixtralSparseMoeBlock.forward with the expert loop replaced by two grouped launches.
+    tp_world > 1: `experts` is this rank's shard; the returned block output is a partial sum the caller
+    all-reduces once (routing and the scatter are replicated on every rank)."""
     shape = hidden_states.shape
     h = hidden_states.reshape(-1, shape[-1])
     T = h.shape[0]
@@ -104,7 +119,7 @@ def sparse_moe_forward(hidden_states: torch.Tensor, gate_weight: torch.Tensor, e
     x_sorted = torch.zeros((m_pad, h.shape[1]), dtype=h.dtype, device=h.device)
     token_of_slot = torch.arange(T, device=h.device).repeat_interleave(top_k)
     x_sorted[dest_row] = h[token_of_slot]
-    y_sorted = experts(x_sorted, group_of_blk)
+    y_sorted = experts(x_sorted, group_of_blk, tp_group=tp_group, tp_world=tp_world)
     weighted = y_sorted[dest_row] * routing.reshape(-1, 1)  # expert output * routing weight, in the activation dtype
     out = torch.zeros_like(h)
     out.index_add_(0, token_of_slot, weighted)

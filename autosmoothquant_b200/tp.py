@@ -72,8 +72,11 @@ def shard_row(module: nn.Module, rank: int, world: int) -> nn.Module:
     lo, hi = _shard_bounds(module.in_features, rank, world, align=16)
     keep_bias = module.use_bias and rank == 0
     if isinstance(module, FP8LinearDynamic):
-        return _shard_fp8(module, slice(None), slice(lo, hi), keep_bias)
+        out = _shard_fp8(module, slice(None), slice(lo, hi), keep_bias)
+        out.full_has_bias = module.use_bias
+        return out
     out = type(module)(hi - lo, module.out_features, keep_bias, module.act_quant)
+    out.full_has_bias = module.use_bias  # every rank must know whether the unsharded module adds a bias
     out.weight = module.weight[:, lo:hi].contiguous()
     if keep_bias:
         out.bias = module.bias.clone()
@@ -144,22 +147,40 @@ class ColumnParallelLinear(nn.Module):
         return y.view(*x.shape[:-1], m.out_features)
 
 
+REDUCE_MODES = ("native", "fp32", "int32", "fused", "fused-native", "nvls")
+
+
 class RowParallelLinear(nn.Module):
     """out / fc2: every rank holds K/p input features; partial outputs are all-reduced (sum).
 
+    reduce =
+      "native"        GEMM launch (partials rounded to the activation dtype) + ncclAllReduce
+      "fp32"          the same with fp32 partials
+      "int32"         exactness mode: int32 accumulators all-reduced over NCCL, then the unsharded module's fp32
+                      epilogue -> bit-identical to the unsharded module
+      "fused"         ONE launch, no NCCL (peer.PeerComm): int32 partials by NVLink peer stores, exact owner-side sum
+                      -> bit-identical to the unsharded module
+      "fused-native"  the same kernel with 16-bit dequantised partials (half the bytes; the numerics of "native")
+      "nvls"          ONE launch: 16-bit partials stay in this rank's symmetric buffer, the tile's owner reduces them
+                      IN THE NVSWITCH (multimem.ld_reduce) and broadcasts the sums (multimem.st); INT8 and FP8
+
     ``has_bias`` tells every rank whether the unsharded module had a bias (only rank 0's shard keeps it).
+    The fused / nvls modes return a tensor that lives in the communicator's double-buffered output; by default it
+    is CLONED so callers may keep it.  ``alias_output=True`` (the benchmark stack, which consumes each result at
+    once) returns the zero-copy view, valid until the launch after the next one on the same communicator.
     """
 
     def __init__(self, shard: nn.Module, group=None, reduce: str = "native", local_scales: bool = False,
-                 backend=CudaBackend, has_bias: Optional[bool] = None, comm=None):
+                 backend=CudaBackend, has_bias: Optional[bool] = None, comm=None, alias_output: bool = False):
         super().__init__()
-        if reduce not in ("native", "fp32", "int32", "fused", "fused-native"):
-            raise ValueError("reduce must be 'native' (activation dtype), 'fp32', 'int32', 'fused' or 'fused-native'")
-        if reduce.startswith("fused") and comm is None:
-            raise ValueError("reduce='fused' needs a peer.PeerComm (GEMM + all-reduce in one kernel over peer memory)")
+        if reduce not in REDUCE_MODES:
+            raise ValueError(f"reduce must be one of {REDUCE_MODES}")
+        if reduce in ("fused", "fused-native", "nvls") and comm is None:
+            raise ValueError(f"reduce={reduce!r} needs a peer.PeerComm (GEMM + all-reduce in one kernel over peer memory)")
         self.comm = comm
         self.shard, self.group, self.reduce, self.local_scales, self.backend = shard, group, reduce, local_scales, backend
-        self.has_bias = shard.use_bias if has_bias is None else has_bias
+        self.alias_output = alias_output
+        self.has_bias = getattr(shard, "full_has_bias", shard.use_bias) if has_bias is None else has_bias
         self.in_features, self.out_features = shard.in_features, shard.out_features
         self._full_bias = None
 
@@ -174,6 +195,49 @@ class RowParallelLinear(nn.Module):
             self._full_bias = b
         return self._full_bias
 
+    def _own(self, y: torch.Tensor) -> torch.Tensor:
+        return y if self.alias_output else y.clone()
+
+    def _act_mode(self):
+        m = self.shard
+        if m.act_quant == "per-token":
+            return (_lib.ACT_PER_TOKEN, 1.0) if self.local_scales else (_lib.ACT_ROW_SCALE_GIVEN, 1.0)
+        if isinstance(m, W8A8BFP32OFP32LinearWithQuantScale):
+            return _lib.ACT_SCALE, float(m.quant_scale.item())
+        return _lib.ACT_ROUND, 1.0
+
+    @torch.no_grad()
+    def forward_q8(self, q: torch.Tensor, row_scale: Optional[torch.Tensor] = None,
+                   out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        """Row-parallel product of activations that are ALREADY int8 (a fused producer quantised them, or forward()
+        did): [M, K/p] int8 -> [M, N] in out_dtype, summed over the ranks.  CUDA only."""
+        m = self.shard
+        ds = float(m.dequant_scale.item())
+        if self.reduce == "fused":
+            return self._own(self.comm.linear_q8_allreduce(q, m.weight, self._bias_everywhere(q.device), ds, row_scale=row_scale))
+        if self.reduce == "fused-native":
+            return self._own(self.comm.linear_q8_allreduce(q, m.weight, m.bias if m.use_bias else None, ds, row_scale=row_scale,
+                                                           partials="native"))
+        if self.reduce == "nvls":
+            return self._own(self.comm.linear_q8_allreduce_nvls(q, m.weight, m.bias if m.use_bias else None, ds, row_scale=row_scale))
+        if self.reduce == "int32":
+            acc = torch.empty((q.shape[0], m.out_features), dtype=torch.int32, device=q.device)
+            _lib.i8gemm_o32(q, m.weight, acc)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+            return self._dequant_i32(acc, ds, row_scale, out_dtype)
+        y = _lib.w8a8_linear_q8(q, m.weight, m.bias if m.use_bias else None, ds, row_scale=row_scale,
+                                out_dtype=torch.float32 if self.reduce == "fp32" else out_dtype)
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+        return y.to(out_dtype)
+
+    def _dequant_i32(self, acc, ds, row_scale, out_dtype):
+        """The unsharded module's epilogue on summed accumulators (linear.py:93,104: factor, * acc, + bias, cast)."""
+        y = (ds * row_scale.view(-1, 1)) * acc if row_scale is not None else ds * acc
+        bias = self._bias_everywhere(y.device)
+        if bias is not None:
+            y = y + bias
+        return y.to(out_dtype)
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.shard
@@ -181,131 +245,98 @@ class RowParallelLinear(nn.Module):
         if isinstance(m, FP8LinearDynamic):
             return self._forward_fp8(m, x, x2)
         row_scale = None
-        if m.act_quant == "per-token":
-            if self.local_scales:
-                mode, qs = _lib.ACT_PER_TOKEN, 1.0
-            else:
-                row_scale = self.backend.local_row_scales(x2)
-                dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)  # = scale of the global row absmax
-                mode, qs = _lib.ACT_ROW_SCALE_GIVEN, 1.0
-        elif isinstance(m, W8A8BFP32OFP32LinearWithQuantScale):
-            mode, qs = _lib.ACT_SCALE, float(m.quant_scale.item())
-        else:
-            mode, qs = _lib.ACT_ROUND, 1.0
+        mode, qs = self._act_mode()
+        if mode == _lib.ACT_ROW_SCALE_GIVEN:
+            row_scale = self.backend.local_row_scales(x2)
+            dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)  # = scale of the global row absmax
+        out_shape = (*x.shape[:-1], m.out_features)
 
-        if self.reduce.startswith("fused"):
-            # ONE launch per rank, no NCCL (peer.PeerComm).  "fused": int32 partials over NVLink peer stores, exact
-            # owner-side sum, the unsharded module's fp32 epilogue -> bit-identical to the unsharded module.
-            # "fused-native": 16-bit dequantised partials (half the bytes) = the numerics of reduce="native".
+        if self.reduce in ("fused", "fused-native", "nvls"):
             if mode == _lib.ACT_PER_TOKEN:
-                raise NotImplementedError("reduce='fused' needs global row scales (local_scales=False)")
+                raise NotImplementedError(f"reduce={self.reduce!r} needs global row scales (local_scales=False)")
             q, _ = _lib.quantize_act(x2, mode, qs, row_scale=row_scale)
-            if self.reduce == "fused":
-                y = self.comm.linear_q8_allreduce(q, m.weight, self._bias_everywhere(x2.device),
-                                                  float(m.dequant_scale.item()), row_scale=row_scale)
-            else:
-                y = self.comm.linear_q8_allreduce(q, m.weight, m.bias if m.use_bias else None,
-                                                  float(m.dequant_scale.item()), row_scale=row_scale, partials="native")
-            return y.view(*x.shape[:-1], m.out_features)
+            return self.forward_q8(q, row_scale, x.dtype).view(out_shape)
 
         if self.reduce == "int32":
             # exactness mode: sum the integer accumulators, then the unsharded module's fp32 epilogue
             acc = self.backend.int32_partial(m, x2, mode, qs, row_scale)
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
-            ds = float(m.dequant_scale.item())
-            y = (ds * row_scale.view(-1, 1)) * acc if row_scale is not None else ds * acc
-            bias = self._bias_everywhere(y.device)
-            if bias is not None:
-                y = y + bias
-            return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
+            return self._dequant_i32(acc, float(m.dequant_scale.item()), row_scale, x.dtype).view(out_shape)
 
         y = self.backend.linear(m, x2, mode, qs, row_scale)
         if self.reduce == "fp32" and y.dtype != torch.float32:
             y = y.float()
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
-        return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
+        return y.to(x.dtype).view(out_shape)
+
+    def _forward_fp8(self, m: FP8LinearDynamic, x: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        """FP8 per-token row-parallel (config 5): the per-token scale is absmax(row over the WHOLE K) / 448, so the
+        local scales are max-all-reduced and the kernel quantises with the supplied scales; fp32-accumulated partial
+        products are rounded to the activation dtype (or kept fp32, reduce="fp32") and summed by one all-reduce, or
+        — reduce="nvls" — reduced in the switch by the fused kernel."""
+        if m.act_quant != "per-token" or self.reduce in ("int32", "fused", "fused-native"):
+            raise NotImplementedError("FP8 row-parallel: per-token activations with reduce='native', 'fp32' or 'nvls'")
+        row_scale = self.backend.fp8_local_row_scales(x2)
+        if not self.local_scales:
+            dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)
+        out_shape = (*x.shape[:-1], m.out_features)
+        if self.reduce == "nvls":
+            q, _ = _lib.quantize_act(x2, _lib.ACT_ROW_SCALE_GIVEN, fp8=True, row_scale=row_scale)
+            y = self.comm.linear_q8_allreduce_nvls(q, m.weight, m._bias_f32(), float(m.weight_scale.item()), row_scale=row_scale,
+                                                   out_dtype=x.dtype if x.dtype != torch.float32 else torch.bfloat16)
+            return self._own(y).to(x.dtype).view(out_shape)
+        y = self.backend.fp8_linear_given_scales(m, x2, row_scale, self.reduce == "fp32")
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+        return y.to(x.dtype).view(out_shape)
 
 
-def _rowparallel_forward_fp8(self, m: FP8LinearDynamic, x: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
-    """FP8 per-token row-parallel (config 5): the per-token scale is absmax(row over the WHOLE K) / 448, so the local
-    scales are max-all-reduced and the kernel quantises with the supplied scales; fp32-accumulated partial
-    products are rounded to the activation dtype (or kept fp32, reduce="fp32") and summed by one all-reduce."""
-    if m.act_quant != "per-token" or self.reduce in ("int32", "fused"):
-        raise NotImplementedError("FP8 row-parallel: per-token activations with reduce='native' or 'fp32' only")
-    row_scale = self.backend.fp8_local_row_scales(x2)
-    if not self.local_scales:
-        dist.all_reduce(row_scale, op=dist.ReduceOp.MAX, group=self.group)
-    y = self.backend.fp8_linear_given_scales(m, x2, row_scale, self.reduce == "fp32")
-    dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
-    return y.to(x.dtype).view(*x.shape[:-1], m.out_features)
-
-
-RowParallelLinear._forward_fp8 = _rowparallel_forward_fp8
-
-
-def _shard_fused_columns(fused, rank: int, world: int, device):
-    """Column shard of a fused W_pack module (q|k|v or gate|up): every block is split separately so rank r
-    holds [q_r; k_r; v_r] (its own heads) and the per-block dequant scales stay valid."""
-    from .layers.nn.linear import W8A8BFP32OFP32QKVLinear
-
-    sizes = fused.qkv_size
-    local_sizes, rows = [], []
-    start = 0
-    for n in sizes:
-        if n % world:
-            raise ValueError(f"block of {n} output features is not divisible by world {world}")
-        step = n // world
-        rows.append(fused.weight[start + rank * step:start + (rank + 1) * step])
-        local_sizes.append(step)
-        start += n
-    out = W8A8BFP32OFP32QKVLinear(local_sizes, fused.in_features, sum(local_sizes), fused.use_bias, fused.act_quant)
-    out.weight = torch.cat(rows, dim=0).contiguous()
-    for name in fused._scale_names:
-        setattr(out, name, getattr(fused, name).clone())
-    if fused.use_bias:
-        start, parts = 0, []
-        for n in sizes:
-            step = n // world
-            parts.append(fused.bias[start + rank * step:start + (rank + 1) * step])
-            start += n
-        out.bias = torch.cat(parts).contiguous()
-    return out.to(device)
+TP_REDUCE_CHOICES = ("nccl", "nccl-int32", "fused", "fused-int32", "nvls")
 
 
 def build_tp_decoder(cfg, layers, device, world: int, rank: int, quant_config: Optional[Dict[str, str]] = None,
-                     group=None, dtype=torch.bfloat16, seed: int = 0, glue: bool = True, fused_allreduce: bool = False,
-                     max_tokens: int = 2048, partials: str = "int32"):
-    """The benchmark stack of ``harness.QuantDecoder`` tensor-parallel over `world` ranks: fused q|k|v and
-    gate|up column-sharded by head / by intermediate channel, o_proj and down_proj row-sharded with ONE
-    all-reduce each (NCCL over NVLink), attention over the local heads, residual stream and norms replicated.
-    Every rank builds the same seeded full-size layer and keeps its shard (one layer at a time).
-    fused_allreduce=True replaces (GEMM launch + NCCL all-reduce) of the two row-parallel projections by the
-    single-launch peer-memory kernel of ``peer.PeerComm`` (``max_tokens`` = largest batch*seq it will see)."""
+                     group=None, dtype=torch.bfloat16, seed: int = 0, glue: bool = True, tp_reduce: str = "nccl",
+                     max_tokens: int = 2048, fused_allreduce: Optional[bool] = None, partials: Optional[str] = None):
+    """The benchmark stack of ``harness.QuantDecoder`` tensor-parallel over `world` ranks: q|k|v and gate|up (or
+    every expert's w1 / w3) column-sharded by head / by intermediate channel, o_proj and down_proj (w2) row-sharded
+    with ONE all-reduce each, attention over the local heads, residual stream, norms and routing replicated.
+    Every rank draws the same seeded full-size weights and keeps its shard, one projection at a time.
+    tp_reduce picks the row-parallel reduction:
+      "nccl"         GEMM launch + ncclAllReduce in the activation dtype
+      "nccl-int32"   int32 accumulators over NCCL: bit-identical to the unsharded stack (parity gate)
+      "fused-int32"  one launch, int32 partials over NVLink peer stores: bit-identical to the unsharded stack
+      "fused"        the same kernel with 16-bit partials (NCCL-native numerics)
+      "nvls"         one launch, in-switch reduction (multimem.ld_reduce / multimem.st); INT8 and FP8
+    ``max_tokens`` = largest batch*seq the communicator's buffers will see."""
     from . import harness
 
+    if fused_allreduce is not None:  # round-1 keyword pair
+        tp_reduce = ("fused-int32" if (partials or "int32") == "int32" else "fused") if fused_allreduce else "nccl"
+    if tp_reduce not in TP_REDUCE_CHOICES:
+        raise ValueError(f"tp_reduce must be one of {TP_REDUCE_CHOICES}")
     model = harness.QuantDecoder(cfg, quant_config, device=device, dtype=dtype, seed=seed, layers=layers,
-                                 fuse_projections=True, glue=glue, swiglu_epilogue=False)
-    if model.qcfg["type"] != "int8":
-        raise NotImplementedError("tensor-parallel fp8 stack")
+                                 fuse_projections=True, glue=glue, tp=(rank, world))
+    fp8 = model.qcfg["type"] != "int8"
+    if fp8 and tp_reduce in ("nccl-int32", "fused", "fused-int32"):
+        raise NotImplementedError("the FP8 stack reduces over NCCL ('nccl') or in the switch ('nvls'): there is no integer partial")
     comm = None
-    if fused_allreduce and world > 1:
+    if tp_reduce in ("fused", "fused-int32", "nvls") and world > 1:
         from .peer import PeerComm
 
-        comm = PeerComm(group=group, device=device, max_m=max_tokens, max_n=cfg.hidden, dtype=dtype)
+        comm = PeerComm(group=group, device=device, max_m=max_tokens, max_n=cfg.hidden, dtype=dtype, nvls=tp_reduce == "nvls",
+                        p2p=tp_reduce != "nvls")
     model.peer_comm = comm
+    reduce = {"nccl": "native", "nccl-int32": "int32", "fused": "fused-native", "fused-int32": "fused", "nvls": "nvls"}[tp_reduce]
     for layer in model.layers:
-        layer.qkv_proj = _shard_fused_columns(layer.qkv_proj, rank, world, device)
-        layer.qkv_sizes = list(layer.qkv_proj.qkv_size)
-        layer.gate_up_proj = _shard_fused_columns(layer.gate_up_proj, rank, world, device)
-        if model.glue and (cfg.intermediate // world) % 32 == 0:
-            layer.enable_swiglu_epilogue()  # interleave the LOCAL gate / up rows for the SwiGLU epilogue
-        for name in ("o_proj", "down_proj"):
-            full = getattr(layer, name)
-            setattr(layer, name, RowParallelLinear(shard_row(full, rank, world).to(device), group=group,
-                                                   has_bias=full.use_bias,
-                                                   reduce=("fused" if partials == "int32" else "fused-native") if comm is not None else "native",
-                                                   comm=comm))
-        layer.tp_world, layer.tp_group, layer.peer_comm, layer.peer_partials = world, group, comm, partials
-        torch.cuda.empty_cache()
+        rows = ("o_proj",) if layer.moe is not None else ("o_proj", "down_proj")
+        for name in rows:
+            shard = getattr(layer, name)
+            setattr(layer, name, RowParallelLinear(shard, group=group,
+                                                   reduce=reduce, comm=comm, alias_output=True))
+        if not layer.fused:  # module path (FP8): column-parallel wrappers keep the module forward, outputs stay sharded
+            cols = ("q_proj", "k_proj", "v_proj") + (() if layer.moe is not None else ("gate_proj", "up_proj"))
+            for name in cols:
+                setattr(layer, name, ColumnParallelLinear(getattr(layer, name)))
+        layer.tp_world, layer.tp_group, layer.peer_comm = world, group, comm
     model.tp_world = world
+    model.tp_reduce = tp_reduce
     return model

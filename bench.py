@@ -1,28 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the B200 W8A8 linear path at model level (BASELINE.json metric).
+"""Benchmark of the B200 W8A8 / FP8 linear path at model level (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 2|3|4|5]
 
-Metric: Llama-2-7B INT8 (all linears per-tensor) prefill tokens/s, batch 1 x seq 2048 per GPU,
-synthetic prompts and seeded synthetic weights of the true shapes.  One "step" is one prefill
-forward of the whole 32-layer stack; every quantized projection is one launch of the fused sm_100a
-kernel through the reference-facing module API (autosmoothquant_b200.layers.nn.linear).
+Default workload (BASELINE configs[1]): Llama-2-7B INT8, all linears per-tensor, synthetic seq-2048 prompts, seeded
+synthetic weights of the true shapes.  One "step" is one prefill forward of the whole 32-layer stack; every quantized
+projection is one launch of the fused sm_100a kernel.
 
-  value     device-timed tokens/s with the prompt already resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the public API with HOST inputs: pinned input_ids -> H2D -> forward ->
-            last-token logits D2H, every step, inside the timed region
-  roofline  INT8 tensor-core roofline of the dominant kernel (asq_linear_kernel): algorithmic
-            2*M*N*K ops of all quantized-linear launches of a step / their CUDA-event durations
-  cpu_baseline  the CPU oracle (numpy restatement of the reference forward) on the host cores, on a
-            bounded sample (one decoder layer's seven linears at seq 2048, scaled by the layer count)
+  N = 1    one GPU, batch 1 x 2048 tokens
+  N > 1    TENSOR PARALLEL by default (north_star: qkv / fc1 column-sharded, out / fc2 row-sharded, one all-reduce per
+           row-parallel output over NVLink), weak scaling: the global batch is N sequences, every rank works on all of
+           them.  Before timing, the run checks ON DEVICE that the tensor-parallel stack in the exact int32 mode is
+           bit-equal to the unsharded stack on a 2-layer slice ("tp_parity").  `--parallel dp` measures N independent
+           replicas instead (no data-path collective); the default run reports that number too (dp_replicas_tokens_s).
 
-Multi-GPU (torchrun, one rank per GPU): data-parallel replicas — every rank runs its own prompt
-through its own copy of the 7B stack (6.6 GB of int8 weights), no data-path collective, weak scaling.
-The tensor-parallel variant of the same stack (column/row sharded linears + one NCCL all-reduce per
-row-parallel output, autosmoothquant_b200.tp) is measured with --parallel tp.
+  value     device-timed tokens/s, prompts resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public API with HOST inputs: pinned input_ids -> H2D -> forward -> last-token
+            logits D2H, every step, inside the timed region
+  roofline  INT8 tensor-core roofline of the dominant kernel (asq_linear_kernel): algorithmic 2*M*N*K ops of the
+            quantized-linear launches of a step / their CUDA-event durations
+  module_path  (N = 1) tokens/s of the SAME stack through the drop-in module API only: 7 Linear.forward calls per
+            layer, torch norms / RoPE / SiLU, no producer fusion
+  collective   (N > 1) which all-reduce ran, its share of the step, NVLink bytes per GPU per step
+  cpu_baseline the reference's unmodified Linear classes (baseline/_ref) on the host cores, bounded sample
 
---impl reference times the CPU oracle port of the reference's forward on all host threads (the
-reference has no CPU path of its own: its only native code is a cuBLASLt wrapper).
+--impl reference runs the reference's OWN Python forward — the unmodified autosmoothquant/layers/nn/linear.py classes
+from baseline/_ref with the exact-integer `_CUDA` stub of oracle/gen_golden.py — on the host cores, fp32 activations,
+all threads it can use (set explicitly; torchrun's OMP_NUM_THREADS=1 is overridden and the count is printed).
 """
 from __future__ import annotations
 
@@ -38,8 +42,16 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "Llama-2-7B INT8 prefill tokens/sec (seq=2048, batch=1 per GPU, all linears per-tensor)"
 UNIT = "tokens/s"
+
+# BASELINE.json configs (index = position in `configs`; 1 is the OPT-125M CPU plumbing case of tests/test_offline_pipeline.py)
+PRESETS = {
+    2: dict(model="llama-2-7b", quant="", batch=1, seq=2048),
+    3: dict(model="llama-2-13b", quant="out=per-token,fc2=per-token", batch=32, seq=2048, parallel="dp"),
+    4: dict(model="mixtral-8x7b", quant="fc1=per-token,fc2=per-token", batch=1, seq=2048, global_batch=1),
+    5: dict(model="llama-2-70b", quant="type=fp8,qkv=per-token,out=per-token,fc1=per-token,fc2=per-token", batch=1, seq=2048,
+            global_batch=1),
+}
 
 
 def parse_args():
@@ -48,58 +60,197 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="llama-2-7b")
-    ap.add_argument("--seq", type=int, default=2048)
-    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(PRESETS),
+                    help="BASELINE.json configuration: 2 Llama-2-7B per-tensor (default, the metric's), 3 Llama-2-13B out/fc2 "
+                         "per-token batch 32 (1 GPU), 4 Mixtral-8x7B per-token experts TP, 5 Llama-2-70B FP8 per-token TP")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--seq", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (weak scaling)")
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
-    ap.add_argument("--parallel", default="dp", choices=["dp", "tp"])
-    ap.add_argument("--quant", default="",
-                    help="quant_config overrides, e.g. 'out=per-token,fc2=per-token' (BASELINE config 3); default: all per-tensor")
-    ap.add_argument("--tp-reduce", default="auto", choices=["auto", "fused", "fused-int32", "nccl"],
-                    help="--parallel tp: row-parallel GEMM fused with its all-reduce over peer memory (one launch), "
-                         "(16-bit partials = NCCL-native numerics; fused-int32 = exact integer partials), or GEMM launch + NCCL "
-                         "all-reduce; auto = fused at 2 GPUs (measured faster), NCCL (NVLS) beyond")
+    ap.add_argument("--parallel", default=None, choices=["dp", "tp"], help="default: tp when N > 1")
+    ap.add_argument("--quant", default=None,
+                    help="quant_config overrides, e.g. 'out=per-token,fc2=per-token'; default: the preset's")
+    ap.add_argument("--tp-reduce", default="auto", choices=["auto", "nccl", "nccl-int32", "fused", "fused-int32", "nvls"],
+                    help="row-parallel reduction: nvls = GEMM fused with an in-switch all-reduce (multimem.ld_reduce/st), "
+                         "fused / fused-int32 = GEMM fused with NVLink peer stores (16-bit / exact int32 partials), "
+                         "nccl = GEMM launch + ncclAllReduce; auto = nvls when the system has NVLS multicast, else nccl")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip module_path / dp_replicas / reference_native_gpu")
+    ap.add_argument("--no-parity", action="store_true", help="skip the tp_parity gate (debugging only)")
     ap.add_argument("--no-glue", action="store_true",
                     help="module path only: torch norms / RoPE / SiLU, every linear quantises its own input")
     ap.add_argument("--no-fuse", action="store_true",
                     help="one launch per projection (q,k,v,gate,up separately) instead of the fused-W_pack module")
-    return ap.parse_args()
+    args = ap.parse_args()
+    preset = PRESETS[args.config]
+    for key in ("model", "seq", "batch", "quant"):
+        if getattr(args, key) is None:
+            setattr(args, key, preset[key])
+    args.fixed_global_batch = preset.get("global_batch") if args.parallel != "dp" else None
+    if args.parallel is None:
+        args.parallel = preset.get("parallel")
+    return args
 
 
-# ----------------------------------------------------------------------------- CPU oracle legs
-def cpu_layer_sample(cfg, seq, threads):
-    """Time the oracle port of one decoder layer's seven quantized linears (per-tensor INT8) on the host."""
-    import numpy as np
+def quant_overrides(args):
+    out = {}
+    for item in filter(None, (s.strip() for s in args.quant.split(","))):
+        key, _, val = item.partition("=")
+        out[key.strip()] = val.strip()
+    return out
 
-    from oracle import w8a8_oracle as O
 
-    rng = np.random.default_rng(0)
-    h, inter = cfg.hidden, cfg.intermediate
-    kv = cfg.kv_heads * cfg.head_dim
-    shapes = [("qkv", h, h), ("qkv", kv, h), ("qkv", kv, h), ("out", h, h), ("fc1", inter, h), ("fc1", inter, h),
-              ("fc2", h, inter)]
-    weights = {}
-    t_total = 0.0
-    for kind, n, k in shapes:
-        key = (n, k)
-        if key not in weights:
-            weights[key] = rng.integers(-127, 128, size=(n, k), dtype=np.int8)
-        w = weights[key]
-        x = (rng.standard_normal((seq, k)).astype(np.float32) * (30.0 if kind in ("qkv", "fc1") else 1.0))
-        x = O.round_to(x, "bf16")
-        t0 = time.perf_counter()
-        if kind in ("qkv", "fc1"):
-            O.w8a8_linear(x, "bf16", w, 0.003, act_quant="per-tensor")
+def granularity_label(args):
+    qc = {"qkv": "per-tensor", "out": "per-tensor", "fc1": "per-tensor", "fc2": "per-tensor", "type": "int8"}
+    qc.update(quant_overrides(args))
+    kind = "INT8" if qc["type"] == "int8" else "FP8-e4m3"
+    if all(qc[k] == "per-tensor" for k in ("qkv", "out", "fc1", "fc2")):
+        return f"all linears per-tensor {kind} (quant_config qkv/out/fc1/fc2=per-tensor)"
+    return f"{kind}, quant_config " + "/".join(f"{k}={qc[k]}" for k in ("qkv", "out", "fc1", "fc2"))
+
+
+def metric_name(args, cfg):
+    if args.config == 2 and args.model == "llama-2-7b":
+        return "Llama-2-7B INT8 prefill tokens/sec (seq=2048, batch=1 per GPU, all linears per-tensor)"
+    return f"{cfg.name} {granularity_label(args)} prefill tokens/sec (seq={args.seq})"
+
+
+def workload_config(args, cfg, layers, world):
+    """`config` of the JSON line: the SAME dict in both arms (the driver compares them); everything specific to how
+    an arm executes the workload goes into `details`."""
+    tp = world > 1 and (args.parallel or "tp") == "tp"
+    global_batch = (args.fixed_global_batch or args.batch * world) if tp else args.batch * world
+    return {
+        "workload": f"{cfg.name} prefill, {granularity_label(args)}, batch {args.batch} x seq {args.seq} per GPU, "
+                    f"synthetic prompts and seeded weights",
+        "baseline_config": args.config, "layers": layers, "seq_len": args.seq, "batch_per_gpu": args.batch,
+        "global_batch": global_batch, "parallelism": f"tp{world}" if tp else f"dp{world}",
+        "l2": "weights and activations stream through the 126 MB L2 every step: inputs larger than L2",
+    }
+
+
+# ----------------------------------------------------------------------------- the reference's own forward (CPU)
+def _set_host_threads():
+    """All host threads for the CPU arm, set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    import torch
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(n)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def load_reference_linear():
+    """The reference's layers/nn/linear.py, unmodified, imported from baseline/_ref (copied there from /root/reference
+    by __graft_entry__.build(); git-ignored, travels to the GPU box) with the `_CUDA` stub whose GEMM is the exact
+    integer matmul (oracle/gen_golden.py: the same stub the golden vectors were generated with)."""
+    from oracle import gen_golden
+
+    ref_root = ROOT / "baseline" / "_ref"
+    if not (ref_root / "autosmoothquant" / "layers" / "nn" / "linear.py").exists():
+        raise FileNotFoundError(f"{ref_root} holds no copy of the reference's layers package (run __graft_entry__.build() "
+                                "where /root/reference exists)")
+    return gen_golden.import_reference(str(ref_root))
+
+
+def reference_layer_modules(L, cfg, qc, seed=0):
+    """The seven projections of one decoder layer as the reference's model classes build them
+    (models/llama.py:74-106, 185-214), converted by the reference's own from_float from seeded fp32 weights."""
+    import torch
+
+    h, inter, kv = cfg.hidden, cfg.intermediate, cfg.kv_heads * cfg.head_dim
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(i, o):
+        m = torch.nn.Linear(i, o, bias=False)
+        with torch.no_grad():
+            m.weight.normal_(0.0, 0.02, generator=g)
+        return m
+
+    plan = [("qkv", h, h), ("qkv", h, kv), ("qkv", h, kv), ("out", h, h), ("fc1", h, inter), ("fc1", h, inter), ("fc2", inter, h)]
+    mods = []
+    for kind, i, o in plan:
+        if qc.get("type", "int8") != "int8":
+            m = L.FP8LinearDynamic(i, o, "per-token")  # what the model constructors build (llama.py:83-90)
+            src = L.FP8LinearDynamic.from_float(lin(i, o), 1.0)
+            m.weight, m.weight_scale = src.weight, src.weight_scale
+        elif kind in ("qkv", "fc1"):
+            m = L.W8A8BFP32OFP32Linear.from_float(lin(i, o), 4.5 / 127, act_quant=qc[kind])
         else:
-            O.w8a8_linear(x, "bf16", w, 0.003, act_quant="per-tensor", quant_scale=0.05)
-        t_total += time.perf_counter() - t0
-    return t_total
+            m = L.W8A8BFP32OFP32LinearWithQuantScale.from_float(lin(i, o), 6.0 / 127, act_quant=qc[kind])
+        mods.append((kind, m))
+    return mods
 
 
-def reference_native_gpu_sample(cfg, seq, layers):
-    """The reference's OWN hot path on this GPU, as a second baseline next to the CPU one: the eager launches of
+def reference_cpu_layer_step(mods, tokens, seed=1):
+    """One bounded sample: the seven Linear.forward calls of ONE decoder layer on `tokens` rows, fp32 activations
+    (the reference's default dtype, examples/test_model.py:31-33).  Returns seconds."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(tokens, m.in_features, generator=g) * (30.0 if kind in ("qkv", "fc1") else 1.0) for kind, m in mods]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for (kind, m), x in zip(mods, xs):
+            m(x)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_measure(args, cfg, layers, steps, warmup):
+    threads = _set_host_threads()
+    qc = {"qkv": "per-tensor", "out": "per-tensor", "fc1": "per-tensor", "fc2": "per-tensor", "type": "int8"}
+    qc.update(quant_overrides(args))
+    if qc["type"] == "fp8":
+        qc["type"] = "fp8_e4m3"
+    try:
+        L = load_reference_linear()
+        kind = "reference"
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"reference classes not importable: {e!r}"[:300], "kind": "reference", "cores": threads}
+    mods = reference_layer_modules(L, cfg, qc)
+    tokens = args.seq  # one sequence of the workload
+    for _ in range(warmup):
+        reference_cpu_layer_step(mods, tokens)
+    times = [reference_cpu_layer_step(mods, tokens) for _ in range(steps)]
+    t_layer = statistics.median(times)
+    moe = cfg.top_k if cfg.experts else 1  # a Mixtral token visits top_k experts' fc1 / fc2
+    scale = layers * (1 if not cfg.experts else (4 + 3 * moe) / 7.0)
+    return {
+        "value": tokens / (t_layer * scale), "unit": UNIT, "cores": threads, "kind": kind, "t_layer_s": t_layer,
+        "steps": steps, "scaled_by": scale,
+        "sample": f"each step = the reference's unmodified Linear.forward (baseline/_ref, exact-integer _CUDA stub) for the 7 "
+                  f"projections of ONE decoder layer on {tokens} tokens, fp32 activations, {threads} torch threads; "
+                  f"tokens/s = {tokens} / (median step x {scale:g} layers); attention / norms excluded (favours the CPU)",
+    }
+
+
+def run_reference(args, cfg, layers):
+    """--impl reference: rank 0 only; every step is a bounded sample (one decoder layer), ms_per_step is MEASURED."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)  # exactly K timed steps after W warm-up steps, as the GPU arm
+    t0 = time.perf_counter()
+    cb = cpu_reference_measure(args, cfg, layers, steps, warmup)
+    if "unavailable" in cb:
+        print(json.dumps({"impl": "reference", "unavailable": cb["unavailable"]}))
+        return
+    line = {
+        "impl": "reference", "metric": metric_name(args, cfg), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": cb["t_layer_s"] * 1e3, "scaled_by": cb["scaled_by"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8" if "fp8" not in args.quant else "fp8_e4m3",
+        "data": "synthetic", "config": workload_config(args, cfg, layers, int(os.environ.get("WORLD_SIZE", "1"))),
+        "device": "host CPU", "wall_s": time.perf_counter() - t0,
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "a step is one decoder layer's quantized linears (bounded sample); value extrapolates it to the whole stack "
+                "(x scaled_by) and is per host, not per GPU",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def reference_native_gpu_sample(cfg, seq, layers, dev):
+    """The reference's OWN hot path on this GPU, the like-for-like baseline: the eager launches of
     W8A8BFP32OFP32Linear(.WithQuantScale).forward (linear.py:83-106, 278-302) around the reference's unmodified
     native GEMM (oracle/_ref = csrc/int8gemm built by oracle/build_ref.py), seven separate projections per
     decoder layer as the reference's model classes issue them.  Linears only, bf16 activations."""
@@ -107,9 +258,8 @@ def reference_native_gpu_sample(cfg, seq, layers):
 
     from oracle import build_ref
 
-    if not (torch.cuda.is_available() and build_ref.available()):
+    if not build_ref.available():
         return None
-    dev = torch.device("cuda", torch.cuda.current_device())
     gemm = build_ref.load().I8CUGEMM()
     h, inter, kv = cfg.hidden, cfg.intermediate, cfg.kv_heads * cfg.head_dim
     shapes = [(h, h, None), (kv, h, None), (kv, h, None), (h, h, 0.05), (inter, h, None), (inter, h, None), (h, inter, 0.06)]
@@ -127,6 +277,8 @@ def reference_native_gpu_sample(cfg, seq, layers):
     for _ in range(3):
         layer()
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 10
     e0.record()
@@ -134,58 +286,12 @@ def reference_native_gpu_sample(cfg, seq, layers):
         layer()
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     t_layer = e0.elapsed_time(e1) / iters * 1e-3
     ops = 2.0 * seq * sum(n * k for n, k, _ in shapes)
-    return {"linears_ms_per_step": t_layer * layers * 1e3, "tops": ops / t_layer / 1e12,
+    return {"linears_ms_per_step": t_layer * layers * 1e3, "tops": ops / t_layer / 1e12, "clocks": clocks,
             "what": "reference eager prologue/epilogue + its own cuBLASLt INT8 GEMM (oracle/_ref) on this GPU, "
                     f"7 projections/layer x {layers} layers, quantized linears only"}
-
-
-def cpu_baseline(cfg, seq, layers):
-    threads = os.cpu_count() or 1
-    t_layer = cpu_layer_sample(cfg, seq, threads)
-    extra = {}
-    try:
-        ref_gpu = reference_native_gpu_sample(cfg, seq, layers)
-        if ref_gpu is not None:
-            extra["reference_native_gpu"] = ref_gpu
-    except Exception as e:  # noqa: BLE001
-        extra["reference_native_gpu"] = {"unavailable": repr(e)[:200]}
-    return {
-        **extra,
-        "value": seq / (t_layer * layers),
-        "unit": UNIT,
-        "cores": threads,
-        "kind": "port",
-        "sample": f"oracle (numpy) forward of the 7 quantized linears of ONE decoder layer at seq {seq} "
-                  f"({t_layer:.2f} s), scaled x{layers} layers; attention/norms excluded (favours the CPU)",
-    }
-
-
-def run_reference(args, cfg, layers):
-    """--impl reference: the CPU oracle port on the host cores, same metric/config; rank 0 only."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    times = []
-    for _ in range(args.warmup and 1):
-        cpu_layer_sample(cfg, args.seq, os.cpu_count())
-    for _ in range(max(1, min(args.steps, 3))):
-        times.append(cpu_layer_sample(cfg, args.seq, os.cpu_count()))
-    t_layer = statistics.median(times)
-    value = args.seq * args.batch / (t_layer * layers)
-    cb = {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-          "sample": f"each step = oracle forward of one decoder layer's 7 quantized linears at seq {args.seq}, "
-                    f"scaled x{layers}; median of {len(times)} steps"}
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": 1, "ms_per_step": t_layer * layers * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": f"{cfg.name} prefill, {granularity_label(args)}, "
-                               f"batch {args.batch} x seq {args.seq} per GPU, bf16 activations",
-                   "device": "host CPU (oracle port of the quantized linears)", "layers": layers},
-        "cpu_baseline": cb,
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -207,10 +313,7 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8: "hw_slowdown",
-                0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-            }
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
             while not self._stop_evt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
@@ -234,29 +337,133 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def quant_overrides(args):
-    out = {}
-    for item in filter(None, (s.strip() for s in args.quant.split(","))):
-        key, _, val = item.partition("=")
-        out[key.strip()] = val.strip()
+# ----------------------------------------------------------------------------- GPU arm
+def _physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            pass
+    return local_rank
+
+
+def pick_tp_reduce(args, world, dev, fp8):
+    """auto: the in-switch fused kernel when this system exposes an NVLS multicast address, else NCCL."""
+    if args.tp_reduce != "auto":
+        return args.tp_reduce, None
+    import torch
+    import torch.distributed as dist
+
+    ok = torch.zeros(1, device=dev)
+    why = None
+    try:
+        import torch.distributed._symmetric_memory as symm
+
+        t = symm.empty(1 << 20, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(t, dist.group.WORLD.group_name)
+        ok[0] = 1.0 if hdl.multicast_ptr else 0.0
+        if not hdl.multicast_ptr:
+            why = "no NVLS multicast address"
+    except Exception as e:  # noqa: BLE001
+        why = repr(e)[:160]
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return ("nvls" if float(ok) > 0 else "nccl"), why
+
+
+def tp_parity_gate(args, cfg, dev, world, rank, fp8, moe):
+    """On-device parity of the tensor-parallel stack against the unsharded one on a 2-layer slice, before any timing.
+    Dense INT8: the exact modes (int32 accumulators all-reduced over NCCL; int32 partials over NVLink peer stores) must
+    be BIT-EQUAL to the unsharded stack.  FP8 / MoE reduce rounded floating-point partial sums, so they — and the mode
+    that is timed — are held to a stated tolerance instead."""
+    import torch
+    import torch.distributed as dist
+
+    from autosmoothquant_b200.harness import QuantDecoder
+    from autosmoothquant_b200.tp import build_tp_decoder
+
+    qc = quant_overrides(args)
+    S = 256
+    ids = torch.randint(0, cfg.vocab, (max(2, world), S), generator=torch.Generator().manual_seed(99), dtype=torch.int64).to(dev)
+    glue = not args.no_glue
+    ref = QuantDecoder(cfg, qc, device=dev, dtype=torch.bfloat16, seed=0, layers=2, fuse_projections=True, glue=glue)
+    want = ref(ids, last_token_only=False)
+    del ref
+    out = {"slice": f"2 layers, {ids.shape[0]} x {S} tokens, all positions' logits"}
+    scale = float(want.abs().max())
+    modes = []
+    if not fp8 and not moe:
+        modes += [("nccl-int32", True), ("fused-int32", True)]
+    timed = args.tp_reduce
+    if timed not in [m for m, _ in modes]:
+        modes.append((timed, False))
+    ok_all = True
+    for mode, exact in modes:
+        try:
+            m = build_tp_decoder(cfg, layers=2, device=dev, world=world, rank=rank, quant_config=qc, seed=0, glue=glue,
+                                 tp_reduce=mode, max_tokens=ids.numel())
+            got = m(ids, last_token_only=False)
+            torch.cuda.synchronize()
+            diff = float((got - want).abs().max())
+            equal = bool(torch.equal(got, want))
+            if m.peer_comm is not None:
+                m.peer_comm.close()
+            del m
+            tol = 0.0 if exact else 0.08 * scale
+            ok = equal if exact else diff <= tol
+            out[mode] = {"bit_equal": equal, "max_abs_diff": diff, "max_abs_ref": scale,
+                         "required": "bit-equal" if exact else f"max |diff| <= 0.08 x max |ref| (bf16 partial sums over {world} ranks)",
+                         "ok": ok}
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            out[mode] = {"ok": False, "error": repr(e)[:300]}
+        ok_all = ok_all and ok
+    flag = torch.tensor([1.0 if ok_all else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["all_ranks_ok"] = bool(float(flag) > 0)
+    torch.cuda.empty_cache()
     return out
 
 
-def granularity_label(args):
-    qc = {"qkv": "per-tensor", "out": "per-tensor", "fc1": "per-tensor", "fc2": "per-tensor"}
-    qc.update(quant_overrides(args))
-    if all(v == "per-tensor" for v in qc.values()):
-        return "all linears per-tensor INT8 (quant_config qkv/out/fc1/fc2=per-tensor)"
-    return "INT8, quant_config " + "/".join(f"{k}={qc[k]}" for k in ("qkv", "out", "fc1", "fc2"))
+def time_steps(step, steps, barrier):
+    import torch
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) * 1e-3
 
 
-# ----------------------------------------------------------------------------- GPU arm
+def capture_graph(model, ids_dev, logits):
+    import torch
+
+    static_ids = ids_dev.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            model(static_ids)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = model(static_ids)
+    graph.replay()
+    torch.cuda.synchronize()
+    if logits is not None and not torch.equal(static_out, logits):
+        raise RuntimeError("graph replay differs from eager forward")
+    return graph, static_ids, static_out
+
+
 def run_ours(args, cfg, layers):
     import torch
     import torch.distributed as dist
 
     from autosmoothquant_b200 import _lib
-    from autosmoothquant_b200.harness import QuantDecoder, quantized_linear_ops
+    from autosmoothquant_b200.harness import QuantDecoder
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -269,21 +476,37 @@ def run_ours(args, cfg, layers):
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
-    if args.tp_reduce == "auto":
-        args.tp_reduce = "fused" if world == 2 else "nccl"
-    if args.parallel == "tp" and world > 1:
+    parallel = args.parallel or ("tp" if world > 1 else "dp")
+    if world == 1:
+        parallel = "dp"
+    qc = quant_overrides(args)
+    fp8 = qc.get("type", "int8") != "int8"
+    moe = cfg.experts > 0
+    tp = parallel == "tp" and world > 1
+    auto_note = None
+    parity = None
+    if tp:
+        args.tp_reduce, auto_note = pick_tp_reduce(args, world, dev, fp8)
+        if not args.no_parity:
+            parity = tp_parity_gate(args, cfg, dev, world, rank, fp8, moe)
+            if not parity["all_ranks_ok"]:
+                if rank == 0:
+                    print(json.dumps({"error": "tp_parity failed: the tensor-parallel stack does not reproduce the unsharded one",
+                                      "tp_parity": parity}), flush=True)
+                dist.barrier()
+                os._exit(3)
         from autosmoothquant_b200.tp import build_tp_decoder
 
-        model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank, glue=not args.no_glue,
-                                 fused_allreduce=args.tp_reduce.startswith("fused"), max_tokens=args.batch * world * args.seq,
-                                 partials="int32" if args.tp_reduce == "fused-int32" else "native")
-        batch = args.batch * world  # weak scaling: the global batch grows with the GPU count
+        # weak scaling: the global batch grows with the GPU count, every rank sees all of it
+        batch = args.fixed_global_batch or args.batch * world
+        model = build_tp_decoder(cfg, layers=layers, device=dev, world=world, rank=rank, quant_config=qc, glue=not args.no_glue,
+                                 tp_reduce=args.tp_reduce, max_tokens=batch * args.seq)
     else:
-        model = QuantDecoder(cfg, quant_overrides(args), device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
+        model = QuantDecoder(cfg, qc, device=dev, dtype=torch.bfloat16, seed=0, layers=layers,
                              fuse_projections=not args.no_fuse, glue=not args.no_glue)
         batch = args.batch
     B, S = batch, args.seq
-    gen = torch.Generator().manual_seed(1234 + (rank if args.parallel == "dp" else 0))
+    gen = torch.Generator().manual_seed(1234 + (rank if not tp else 0))
     ids_host = torch.randint(0, cfg.vocab, (B, S), generator=gen, dtype=torch.int64).pin_memory()
     ids_dev = ids_host.to(dev)
     out_host = torch.empty((B, 1, cfg.vocab), dtype=torch.float32).pin_memory()
@@ -310,25 +533,16 @@ def run_ours(args, cfg, layers):
         print(json.dumps({"profiled_step": True, "launches_per_step": launches_per_step}))
         return
     graph = None
-    use_graph = not args.no_graph
-    if use_graph:
+    if not args.no_graph:
         try:
-            static_ids = ids_dev.clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    model(static_ids)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = model(static_ids)
-            graph.replay()
-            torch.cuda.synchronize()
-            if not torch.equal(static_out, logits):
-                raise RuntimeError("graph replay differs from eager forward")
+            graph, static_ids, static_out = capture_graph(model, ids_dev, logits)
         except Exception as e:  # noqa: BLE001
             print(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
+            graph = None
+    if world > 1:  # every rank must take the same path (a graph on one rank and eager launches on another would still
+        flag = torch.tensor([1.0 if graph is not None else 0.0], device=dev)  # match, but keep the record honest)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) == 0:
             graph = None
 
     def step_device():
@@ -350,19 +564,13 @@ def run_ours(args, cfg, layers):
     for _ in range(max(args.warmup, 3)):
         step_device()
     # ---- timed region: K steps, device time from CUDA events, barrier + synchronize on both sides
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(_physical_gpu_index(local_rank))
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
+    t_dev = time_steps(step_device, args.steps, barrier)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    t_dev = e0.elapsed_time(e1) * 1e-3
     # ---- end-to-end: host inputs, H2D + forward + D2H per step
     for _ in range(2):
         step_e2e()
@@ -372,73 +580,141 @@ def run_ours(args, cfg, layers):
         step_e2e()
     barrier()
     t_e2e = time.perf_counter() - t0
-    # ---- roofline of the dominant kernel: CUDA events around every asq_linear_kernel launch of one step
-    # (both fused entry points are wrapped at the binding level, so module calls and the producer-fused
-    # path are covered alike)
-    lin_time, lin_ops, n_lin = 0.0, 0.0, 0
-    if True:
-        events = []
-        originals = {name: getattr(_lib, name) for name in ("w8a8_linear", "w8a8_linear_q8", "fp8_linear", "w8a8_gateup_swiglu")}
 
-        def timed(fn):
-            def wrapper(x, weight, *a, **kw):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                out = fn(x, weight, *a, **kw)
-                e.record()
-                events.append((s, e, 2.0 * x.shape[0] * x.shape[1] * weight.shape[0],
-                               (fn.__name__, x.shape[0], weight.shape[0], x.shape[1])))
-                return out
-            return wrapper
+    # ---- roofline of the dominant kernel: CUDA events around every asq_linear_kernel launch of one eager step
+    # (the entry points are wrapped at the binding level, so module calls and the producer-fused path are covered alike)
+    from autosmoothquant_b200 import peer as _peer
 
-        for name, fn in originals.items():
-            setattr(_lib, name, timed(fn))
-        from autosmoothquant_b200 import peer as _peer
+    events = []
 
-        peer_original = _peer.PeerComm.linear_q8_allreduce
-
-        def peer_timed(self, xq, weight, *a, **kw):
+    def timed(fn, label, collective=False):
+        def wrapper(*a, **kw):
+            x = a[1] if collective else a[0]
+            weight = a[2] if collective else a[1]
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            out = peer_original(self, xq, weight, *a, **kw)
+            out = fn(*a, **kw)
             e.record()
-            events.append((s, e, 2.0 * xq.shape[0] * xq.shape[1] * weight.shape[0],
-                           ("linear_q8_allreduce(fused)", xq.shape[0], weight.shape[0], xq.shape[1])))
+            n, rows = weight.shape[0], x.shape[0]
+            if label == "w8a8_grouped_linear":  # stacked expert weights [G*N, K]; x holds the routed slots + padding rows
+                n = weight.shape[0] // a[3].numel()
+                rows = min(rows, B * S * cfg.top_k)
+            events.append((s, e, 2.0 * rows * x.shape[1] * n, (label, rows, n, x.shape[1]), collective))
             return out
+        return wrapper
 
-        _peer.PeerComm.linear_q8_allreduce = peer_timed
-        try:
-            model(ids_dev)  # one warm instrumented pass
-            torch.cuda.synchronize()
-            events.clear()
-            # park the GPU for ~40 ms so the whole step is queued before it starts: the event pairs then
-            # bracket back-to-back kernel executions, not host launch gaps
-            torch.cuda._sleep(int(0.04 * 1.9e9))
-            model(ids_dev)
-            torch.cuda.synchronize()
-        finally:
-            _peer.PeerComm.linear_q8_allreduce = peer_original
-            for name, fn in originals.items():
-                setattr(_lib, name, fn)
-        by_shape = {}
-        for s, e, ops, key in events:
-            dt = s.elapsed_time(e) * 1e-3
+    lib_names = ("w8a8_linear", "w8a8_linear_q8", "fp8_linear", "w8a8_gateup_swiglu", "w8a8_grouped_linear", "i8gemm_o32")
+    originals = {name: getattr(_lib, name) for name in lib_names}
+    peer_originals = {name: getattr(_peer.PeerComm, name) for name in ("linear_q8_allreduce", "linear_q8_allreduce_nvls")}
+    nccl_events = []
+    orig_all_reduce = dist.all_reduce if world > 1 else None
+
+    def timed_all_reduce(t, *a, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_all_reduce(t, *a, **kw)
+        e.record()
+        nccl_events.append((s, e, t.numel() * t.element_size()))
+        return r
+
+    for name, fn in originals.items():
+        setattr(_lib, name, timed(fn, name))
+    for name, fn in peer_originals.items():
+        setattr(_peer.PeerComm, name, timed(fn, name + "(GEMM+all-reduce, one launch)", collective=True))
+    if world > 1:
+        dist.all_reduce = timed_all_reduce
+    try:
+        model(ids_dev)  # one warm instrumented pass
+        torch.cuda.synchronize()
+        events.clear()
+        nccl_events.clear()
+        # park the GPU for ~40 ms so the whole step is queued before it starts: the event pairs then
+        # bracket back-to-back kernel executions, not host launch gaps
+        if world > 1:
+            dist.barrier()
+        torch.cuda._sleep(int(0.04 * 1.9e9))
+        model(ids_dev)
+        torch.cuda.synchronize()
+    finally:
+        for name, fn in peer_originals.items():
+            setattr(_peer.PeerComm, name, fn)
+        for name, fn in originals.items():
+            setattr(_lib, name, fn)
+        if world > 1:
+            dist.all_reduce = orig_all_reduce
+    lin_time = lin_ops = 0.0
+    n_lin = 0
+    coll_time = coll_ops = coll_bytes = 0.0
+    n_coll = 0
+    by_shape = {}
+    for s, e, ops, key, collective in events:
+        dt = s.elapsed_time(e) * 1e-3
+        if collective:
+            coll_time += dt
+            coll_ops += ops
+            coll_bytes += key[1] * key[2] * 2.0
+            n_coll += 1
+        else:
             lin_time += dt
             lin_ops += ops
             n_lin += 1
-            agg = by_shape.setdefault(key, [0, 0.0, 0.0])
-            agg[0] += 1
-            agg[1] += dt
-            agg[2] += ops
+        agg = by_shape.setdefault(key, [0, 0.0, 0.0])
+        agg[0] += 1
+        agg[1] += dt
+        agg[2] += ops
+    nccl_time = sum(s.elapsed_time(e) * 1e-3 for s, e, _ in nccl_events)
+    nccl_bytes = float(sum(b for _, _, b in nccl_events))
+
+    # ---- secondary measurements (fewer steps; never part of `value`)
+    used_graph = graph is not None
+    secondary = {}
+    sec_steps = max(3, min(args.steps, 5))
+    if not args.no_secondary and not tp and world == 1 and not moe and not args.no_glue:
+        try:  # the drop-in module path: 7 Linear.forward per layer, torch glue
+            plain = QuantDecoder(cfg, qc, device=dev, dtype=torch.bfloat16, seed=0, layers=layers, fuse_projections=False, glue=False)
+            for _ in range(3):
+                plain(ids_dev)
+            g2, _, _ = capture_graph(plain, ids_dev, None)
+            for _ in range(2):
+                g2.replay()
+            t_mod = time_steps(g2.replay, sec_steps, barrier)
+            secondary["module_path"] = {
+                "value": B * S * sec_steps / t_mod, "unit": UNIT, "ms_per_step": t_mod / sec_steps * 1e3, "steps": sec_steps,
+                "what": "the same stack through the reference-facing module API only: 7 Linear.forward launches per layer "
+                        "(each quantises its own input in-kernel), torch RMSNorm / RoPE / SiLU / residual adds, CUDA graph"}
+            del g2, plain
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            secondary["module_path"] = {"unavailable": repr(e)[:200]}
+    if not args.no_secondary and tp and args.config == 2:
+        try:  # data-parallel replicas of the same model: N independent prompts, no data-path collective
+            rep = QuantDecoder(cfg, qc, device=dev, dtype=torch.bfloat16, seed=0, layers=layers, fuse_projections=True, glue=True)
+            ids1 = ids_dev[:args.batch].contiguous()
+            for _ in range(3):
+                rep(ids1)
+            g3, _, _ = capture_graph(rep, ids1, None)
+            for _ in range(2):
+                g3.replay()
+            t_rep = time_steps(g3.replay, sec_steps, barrier)
+            tt = torch.tensor([t_rep], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            secondary["dp_replicas_tokens_s"] = args.batch * S * world * sec_steps / float(tt)
+            secondary["dp_replicas_ms_per_step"] = float(tt) / sec_steps * 1e3
+            del g3, rep
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            secondary["dp_replicas_tokens_s"] = None
+            secondary["dp_replicas_error"] = repr(e)[:200]
 
     t = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_dev, t_e2e, t_wall = (float(v) for v in t.tolist())
-    replicas = world if args.parallel == "dp" else 1
+    replicas = world if not tp else 1
     tokens_per_step = B * S * replicas
     value = tokens_per_step * args.steps / t_dev
     e2e_value = tokens_per_step * args.steps / t_e2e
+    step_s = t_dev / args.steps
 
     if rank == 0:
         peaks = {}
@@ -446,53 +722,96 @@ def run_ours(args, cfg, layers):
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:  # noqa: BLE001
             pass
-        bf16_peak = peaks.get("bf16_tflops_sustained")  # kernels are timed inside a long step
-        peak = 2.0 * bf16_peak if bf16_peak else 2.0 * 1400.0
-        peak_src = ("2 x MEASURED_PEAKS.bf16_tflops_sustained (8-bit tensor rate is 2x bf16; no measured int8 figure)"
-                    if bf16_peak else "2 x fallback 1.4 PFLOP/s sustained bf16 (of fallback)")
+        bf16_sus, bf16_burst = peaks.get("bf16_tflops_sustained"), peaks.get("bf16_tflops")
+        peak = 2.0 * bf16_sus if bf16_sus else 2.0 * 1400.0
+        peak_src = ("2 x MEASURED_PEAKS.bf16_tflops_sustained (of measured; the 8-bit tensor rate is 2x bf16, kernels timed inside a long step)"
+                    if bf16_sus else "2 x fallback 1.4 PFLOP/s sustained bf16 (of fallback)")
+        ceiling = None
+        try:
+            ceiling = json.loads((ROOT / "profiles" / "int8_ceiling.json").read_text())
+        except Exception:  # noqa: BLE001
+            pass
         achieved = (lin_ops / lin_time / 1e12) if lin_time > 0 else None
         traffic = None
         try:
             traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
+        par_label = f"tp{world}" if tp else f"dp{world}"
+        config = workload_config(args, cfg, layers, world)
+        assert config["global_batch"] == B * replicas and config["parallelism"] == par_label
+        details = {
+            "cuda_graph": used_graph,
+            "projections": ("q|k|v and gate|up fused per layer (4 GEMM launches/layer)" if getattr(model, "glue", False) or not args.no_fuse
+                            else "one launch per projection (7 launches/layer)"),
+            "glue": ("RMSNorm->int8 producer kernel (asq_glue.cu); RoPE in the q|k|v epilogue; SiLU(gate)*up and down_proj's "
+                     "quantisation in the gate|up epilogue; residual adds in the o_proj / down_proj epilogues (1 GPU); "
+                     "o_proj quantises in-kernel")
+                    if getattr(model, "glue", False)
+                    else "torch norms / RoPE / SiLU; every linear quantises its own input in-kernel",
+            "wall_s_timed_region": t_wall,
+        }
+        if tp:
+            details["tp_reduce"] = args.tp_reduce
+            if auto_note:
+                details["tp_reduce_note"] = auto_note
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {
-                "workload": f"{cfg.name} prefill, {granularity_label(args)}, "
-                            f"batch {args.batch} x seq {S} per GPU, bf16 activations",
-                "layers": layers, "global_batch": B * replicas, "seq_len": S,
-                "parallelism": f"{args.parallel}{world}", "cuda_graph": graph is not None,
-                **({"tp_reduce": args.tp_reduce} if args.parallel == "tp" and world > 1 else {}),
-                "projections": "q|k|v and gate|up fused per layer (4 GEMM launches/layer)"
-                               if not args.no_fuse else "one launch per projection (7 launches/layer)",
-                "glue": ("RMSNorm->int8 producer kernel (asq_glue.cu); RoPE in the q|k|v epilogue; SiLU(gate)*up and down_proj's "
-                         "quantisation in the gate|up epilogue; residual adds in the o_proj / down_proj epilogues; "
-                         "o_proj quantises in-kernel")
-                        if getattr(model, "glue", False)
-                        else "torch norms / RoPE / SiLU; every linear quantises its own input in-kernel",
-                "l2": "weights (6.6 GB int8) and activations stream through the 126 MB L2 every step: inputs larger than L2",
-                "wall_s_timed_region": t_wall,
-            },
-            "clocks": clocks,
+            "metric": metric_name(args, cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp8_e4m3" if fp8 else "int8", "data": "synthetic",
+            "config": config, "details": details, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "asq_linear_kernel<int8,256>", "launches_timed": n_lin,
-                "peak_source": peak_src,
-                "linear_share_of_step": (lin_time / (t_dev / args.steps)) if lin_time else None,
+                "kernel": "asq_linear_kernel (tcgen05 kind::%s, 256x256 CTA-pair tiles)" % ("f8f6f4" if fp8 else "i8"),
+                "launches_timed": n_lin, "peak_source": peak_src,
+                "other_peaks": {"spec_dense_8bit": 4500.0, "2x_bf16_burst_measured": 2.0 * bf16_burst if bf16_burst else None,
+                                "tcgen05_issue_rate_microbench": ceiling},
+                "linear_share_of_step": (lin_time / step_s) if lin_time else None,
+                "per_rank": tp,
                 "by_launch_shape": [{"entry": k[0], "M": k[1], "N": k[2], "K": k[3], "launches": v[0],
                                      "avg_us": v[1] / v[0] * 1e6, "tops": v[2] / v[1] / 1e12}
                                     for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])],
             },
         }
+        if tp:
+            line["tp_parity"] = bool(parity and parity["all_ranks_ok"]) if not args.no_parity else None
+            line["tp_parity_detail"] = parity
+            msg_bytes = coll_bytes + nccl_bytes
+            # in-switch all-reduce of a B-byte message: every GPU sources its B bytes of partials (read by the switch)
+            # plus its 1/N share of the broadcast, and sinks the reduced 1/N share plus the whole broadcast
+            nv_out = msg_bytes * (1.0 + 1.0 / world)
+            coll_t = coll_time + nccl_time
+            line["collective"] = {
+                "tp_reduce": args.tp_reduce,
+                "what": {"nvls": "row-parallel GEMM + in-switch all-reduce in ONE launch (multimem.ld_reduce / multimem.st)",
+                         "fused": "row-parallel GEMM + all-reduce in ONE launch over NVLink peer stores (16-bit partials)",
+                         "fused-int32": "row-parallel GEMM + all-reduce in ONE launch over NVLink peer stores (int32 partials)",
+                         "nccl": "GEMM launch + ncclAllReduce (NVLS)", "nccl-int32": "int32 GEMM + ncclAllReduce"}[args.tp_reduce],
+                "fused_launches_per_step": n_coll, "fused_time_share_of_step": coll_time / step_s if coll_time else 0.0,
+                "nccl_calls_per_step": len(nccl_events), "nccl_time_share_of_step": nccl_time / step_s if nccl_time else 0.0,
+                "allreduce_message_bytes_per_step": msg_bytes,
+                "nvlink_bytes_out_per_gpu_per_step": nv_out,
+                "achieved_gbs_per_direction": nv_out / coll_t / 1e9 if coll_t else None,
+                "peak_gbs_per_direction": 770.0, "peak_source": "measured peer copy per direction, B200_PROFILING.md (900 nominal)",
+                "note": "fused launches time GEMM + collective together; the share includes the row-parallel GEMM's math",
+            }
+        line.update(secondary)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg, S, layers)
+            cb = cpu_reference_measure(args, cfg, layers, steps=3, warmup=1)
+            if not args.no_secondary and not fp8 and not moe:
+                try:
+                    ref_gpu = reference_native_gpu_sample(cfg, S, layers, dev)
+                    if ref_gpu is not None:
+                        line["reference_native_gpu"] = ref_gpu
+                        line["reference_native_gpu"]["ours_linears_ms_per_step"] = lin_time * 1e3
+                        line["reference_native_gpu"]["speedup_linears"] = ref_gpu["linears_ms_per_step"] / (lin_time * 1e3) if lin_time else None
+                except Exception as e:  # noqa: BLE001
+                    line["reference_native_gpu"] = {"unavailable": repr(e)[:200]}
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
         # release the captured graph (it may hold NCCL work) before tearing the communicator down, and never

@@ -216,7 +216,9 @@ int asq_w8a8_gateup_swiglu_q8(const int8_t* xq, const float* row_scale, const in
  * into x [M_pad, K], padding every expert's segment with zero rows to a multiple of 256; group_of_blk[i]
  * (device, int32) names the expert of rows [128 i, 128 i + 128), -1 for unused trailing blocks (skipped).
  *   w_stacked [G * N, K] int8: expert g's weight in rows [g N, (g+1) N); group_dequant_scale [G] (device fp32)
- *   act_mode ROUND | SCALE (per-expert group_quant_scale [G], LinearWithQuantScale) | PER_TOKEN
+ *   act_mode ROUND | SCALE (per-expert group_quant_scale [G], LinearWithQuantScale) | PER_TOKEN |
+ *   ROW_SCALE_GIVEN (row_scale_out then is an INPUT: [M_pad] fp32 scales to quantise with, the tensor-parallel
+ *   w2 whose row absmax spans all ranks' ffn slices)
  *   swiglu != 0: w_stacked holds every expert's w1|w3 in the interleaved layout of asq_w8a8_gateup_swiglu_q8
  *   (N = 2 * ffn), group_dequant_scale / _up are the w1 / w3 scales, y [M_pad, N/2] = T(T(silu(w1 x)) * w3 x).
  * Row results are independent of the other rows, so every real row equals what the expert's own module
@@ -252,6 +254,28 @@ int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const
                                  float dequant_scale, const float* col_scale, void* const* recv_all,
                                  void* const* ctl_all, int rank, int world, int partial16, void* y_multicast,
                                  void* stream);
+
+/* The same row-parallel linear with the sum taken INSIDE THE NVSWITCH (NVLS): the collective an NCCL NVLS
+ * all-reduce performs, fused into the GEMM launch.  Every rank's epilogue TMA-stores its dequantised 16-bit
+ * partial tiles (T(f * acc (+ bias)), the arithmetic of asq_w8a8_linear_q8) into its OWN slice of a symmetric
+ * allocation and bumps a counter on the tile's owner (rank = tile % world); when a tile's counter reaches
+ * `world`, the owner's epilogue warps read the tile through the allocation's multicast address with
+ * multimem.ld_reduce (the switch adds the `world` copies, fp32 accumulation, one rounding to T) and write the
+ * sums to every rank's output with multimem.st.  All ranks walk the tiles in the same order, so tile i's
+ * reduction overlaps tile i+1's MMAs; nothing but 16-byte multimem traffic crosses NVLink.
+ *   xq [M, K/world], w [N, K/world]: int8 (fp8 == 0) or e4m3 (fp8 != 0: kind::f8f6f4, fp32 accumulate — the
+ *       tensor-parallel FP8LinearDynamic of BASELINE config 5); row_scale = GLOBAL per-token scales or NULL
+ *   bias on ONE rank only (it is part of that rank's partial), as for GEMM + ncclAllReduce
+ *   partial_local: this rank's partial buffer [M, N] 16-bit; partial_mc / y_mc: multicast addresses of all
+ *       ranks' partial / output buffers (cuMulticast* or torch symmetric memory, same offset on every rank)
+ *   ctl_all [world]: the control buffers of asq_ar_buffer_bytes (own + asq_ipc_open'ed), zero-filled once
+ * Numerics: those of asq_w8a8_linear_q8 followed by an NVLS ncclAllReduce in T.  Every rank must issue the
+ * same sequence of calls; a launch returns only after every peer has finished writing this rank's output. */
+int asq_q8_linear_allreduce_nvls(const void* xq, int fp8, const float* row_scale, const void* w, const float* bias,
+                                 void* partial_local, const void* partial_mc, void* y_mc, int y_dtype, int64_t M,
+                                 int64_t N, int64_t K, float dequant_scale, const float* col_scale,
+                                 void* const* ctl_all, int rank, int world, void* stream);
+
 /* Zero-filled cudaMalloc memory and CUDA IPC handles (64 bytes) to map it into the other ranks' processes. */
 int asq_dev_alloc(size_t bytes, void** ptr);
 int asq_dev_free(void* ptr);

@@ -31,13 +31,18 @@ OUT_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden"
 DTYPES = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 
 
-def import_reference():
-    """Import the reference's layer modules on CPU (see module docstring)."""
-    if not REFERENCE_ROOT.exists():
-        raise RuntimeError(f"{REFERENCE_ROOT} is not mounted")
+def import_reference(root=None):
+    """Import the reference's layer modules on CPU (see module docstring).  `root` = directory that holds the
+    reference's ``autosmoothquant/`` tree: /root/reference here, or the git-ignored copy of its ``layers`` package
+    under baseline/_ref on the GPU box (bench.py's reference arm).  With `root` given, only the Linear module is returned."""
+    base = Path(root) if root is not None else REFERENCE_ROOT
+    if not base.exists():
+        raise RuntimeError(f"{base} is not mounted")
     if "autosmoothquant.layers.nn.linear" in sys.modules:
+        if root is not None:
+            return sys.modules["autosmoothquant.layers.nn.linear"]
         return sys.modules["autosmoothquant.layers.nn.linear"], sys.modules["autosmoothquant.layers.functional.quantization"]
-    sys.path.insert(0, str(REFERENCE_ROOT))
+    sys.path.insert(0, str(base))
     stub = types.ModuleType("autosmoothquant._CUDA")
 
     class I8CUGEMM:  # int8 [M,K] x int8 [N,K]^T -> int32 [M,N], in place (bindings.cpp:69-84)
@@ -51,6 +56,8 @@ def import_reference():
     torch.cuda.current_device = lambda: "cpu"  # linear.py:101 allocates `out` on current_device()
     import autosmoothquant.layers.nn.linear as ref_linear  # noqa: E402
     import autosmoothquant.layers.functional.quantization as ref_quant  # noqa: E402
+    if root is not None:
+        return ref_linear
     return ref_linear, ref_quant
 
 

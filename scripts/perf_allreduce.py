@@ -35,6 +35,7 @@ def timeit(fn, iters=20, warmup=3):
 Mmax = 2048 * world
 comm = peer.PeerComm(device=dev, max_m=Mmax, max_n=4096)
 comm_mc = peer.PeerComm(device=dev, max_m=Mmax, max_n=4096, multicast=True)
+comm_nv = peer.PeerComm(device=dev, max_m=Mmax, max_n=4096, nvls=True, p2p=False)
 for (M, N, K) in [(2048, 4096, 4096), (2048, 4096, 11008), (Mmax, 4096, 4096), (Mmax, 4096, 11008)]:
     Kl = K // world // 16 * 16
     a = torch.randint(-128, 128, (M, Kl), dtype=torch.int8, device=dev)
@@ -53,10 +54,12 @@ for (M, N, K) in [(2048, 4096, 4096), (2048, 4096, 11008), (Mmax, 4096, 4096), (
     t_fused16 = timeit(lambda: comm.linear_q8_allreduce(a, w, None, 1e-4, partials="native"))
     t_mc = timeit(lambda: comm_mc.linear_q8_allreduce(a, w, None, 1e-4))
     t_mc16 = timeit(lambda: comm_mc.linear_q8_allreduce(a, w, None, 1e-4, partials="native"))
+    t_nv = timeit(lambda: comm_nv.linear_q8_allreduce_nvls(a, w, None, 1e-4))
     if rank == 0:
         print(f"world {world}  {M}x{N}x{K} (K/rank {Kl}): GEMM {t_gemm:6.1f} us | NCCL all-reduce {t_ar:6.1f} us | "
               f"GEMM+NCCL {t_nccl:6.1f} us | fused int32 p2p {t_fused:6.1f} | fused 16-bit p2p {t_fused16:6.1f} | "
-              f"fused int32 multicast {t_mc:6.1f} | fused 16-bit multicast {t_mc16:6.1f} us", flush=True)
+              f"fused int32 multicast {t_mc:6.1f} | fused 16-bit multicast {t_mc16:6.1f} | fused NVLS (in-switch) {t_nv:6.1f} us", flush=True)
+comm_nv.close()
 comm_mc.close()
 comm.close()
 dist.destroy_process_group()

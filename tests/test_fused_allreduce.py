@@ -108,6 +108,60 @@ def _worker(rank, world, port, ret):
                 results[f"{tag} native identical on all ranks {M}x{N}x{K}"] = all(bool(torch.equal(ranks_equal[0], r)) for r in ranks_equal)
         comm_mc.close()
         comm.close()
+        # 5. in-switch all-reduce (multimem.ld_reduce / multimem.st): the numerics of GEMM + bf16 ncclAllReduce.  At
+        # world 2 one fp32 add of two bf16 partials rounded once is the same number whoever computes it -> bit-equal;
+        # beyond, the summation order inside the switch is not NCCL's: equal up to the bf16 rounding of the sum.
+        comm_nv = peer.PeerComm(device=dev, max_m=2048, max_n=4096, nvls=True, p2p=False)
+        for (M, N, K) in SHAPES:
+            a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+            w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(dev)
+            b = torch.randn(N, generator=g).to(dev)
+            rs = (torch.rand(M, generator=g) + 0.5).to(dev)
+            step = K // world // 16 * 16
+            lo, hi = rank * step, (K if rank == world - 1 else (rank + 1) * step)
+            al, wl = a[:, lo:hi].contiguous(), w[:, lo:hi].contiguous()
+            y_nccl = _lib.w8a8_linear_q8(al, wl, b if rank == 0 else None, 3e-5, row_scale=rs)
+            dist.all_reduce(y_nccl)
+            want = _lib.w8a8_linear_q8(a, w, b, 3e-5, row_scale=rs)
+            for rep in range(2):
+                got = comm_nv.linear_q8_allreduce_nvls(al, wl, b if rank == 0 else None, 3e-5, row_scale=rs)
+                torch.cuda.synchronize()
+                if world == 2:
+                    results[f"nvls {M}x{N}x{K} #{rep} == GEMM + NCCL"] = bool(torch.equal(got, y_nccl))
+                else:
+                    results[f"nvls {M}x{N}x{K} #{rep} ~ unsharded"] = bool(torch.allclose(got.float(), want.float(), rtol=2 ** -6,
+                                                                                          atol=2 ** -6 * float(want.float().abs().max())))
+                every = [torch.empty_like(got) for _ in range(world)]
+                dist.all_gather(every, got.clone())
+                results[f"nvls identical on all ranks {M}x{N}x{K} #{rep}"] = all(bool(torch.equal(every[0], r)) for r in every)
+        # FP8-e4m3 twin (BASELINE config 5 row-parallel): e4m3 activations quantised with global row scales
+        M, N, K = 300, 768, 1024
+        x = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+        wf = (torch.randn(N, K, generator=g) * 0.05).to(torch.float8_e4m3fn).to(dev)
+        lo, hi = rank * K // world, (rank + 1) * K // world
+        _, rs = _lib.quantize_act(x, _lib.ACT_PER_TOKEN, fp8=True)  # scales of the whole row
+        ql, _ = _lib.quantize_act(x[:, lo:hi].contiguous(), _lib.ACT_ROW_SCALE_GIVEN, fp8=True, row_scale=rs)
+        wl = wf.view(torch.uint8)[:, lo:hi].contiguous().view(torch.float8_e4m3fn)
+        y_part = _lib.fp8_linear(x[:, lo:hi].contiguous(), wl, None, _lib.ACT_ROW_SCALE_GIVEN, 1.0, 0.5, row_scale_out=rs)
+        dist.all_reduce(y_part)
+        got = comm_nv.linear_q8_allreduce_nvls(ql, wl, None, 0.5, row_scale=rs)
+        torch.cuda.synchronize()
+        results["nvls fp8 == fp8 GEMM + NCCL" if world == 2 else "nvls fp8 ~ fp8 GEMM + NCCL"] = (
+            bool(torch.equal(got, y_part)) if world == 2 else
+            bool(torch.allclose(got.float(), y_part.float(), rtol=2 ** -6, atol=2 ** -6 * float(y_part.float().abs().max()))))
+        # back-to-back launches without host synchronisation, alternating output buffers
+        M, N, K = 512, 1024, 2048
+        a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+        w = torch.randint(-127, 128, (N, K), dtype=torch.int8, generator=g).to(dev)
+        lo, hi = rank * K // world, (rank + 1) * K // world
+        al, wl = a[:, lo:hi].contiguous(), w[:, lo:hi].contiguous()
+        first = comm_nv.linear_q8_allreduce_nvls(al, wl, None, 1e-4).clone()
+        ok = True
+        for _ in range(20):
+            ok = ok and bool(torch.equal(comm_nv.linear_q8_allreduce_nvls(al, wl, None, 1e-4).clone(), first))
+        torch.cuda.synchronize()
+        results["nvls 20 launches back to back"] = ok
+        comm_nv.close()
     except Exception as e:  # noqa: BLE001
         results["exception"] = repr(e)
     finally:

@@ -148,8 +148,8 @@ def _worker_fp8(rank, world, port, ret):
 
         torch.manual_seed(0)
         K, I = 64, 96
-        f1 = FP8LinearDynamic.from_float(torch.nn.Linear(K, I, bias=False), act_quant="per-token")
-        f2 = FP8LinearDynamic.from_float(torch.nn.Linear(I, K, bias=True), act_quant="per-token")
+        f1 = FP8LinearDynamic.from_float(torch.nn.Linear(K, I, bias=False), act_quant="per-token", reference_compat=False)
+        f2 = FP8LinearDynamic.from_float(torch.nn.Linear(I, K, bias=True), act_quant="per-token", reference_compat=False)
         x = torch.randn(5, 4, K)
         col = tp.ColumnParallelLinear(tp.shard_column(f1, rank, world), backend=OracleBackend)
         row = tp.RowParallelLinear(tp.shard_row(f2, rank, world), reduce="fp32", backend=OracleBackend, has_bias=True)
