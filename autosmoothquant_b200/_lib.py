@@ -55,6 +55,7 @@ EXPORTED_SYMBOLS = (
     "asq_ar_buffer_bytes",
     "asq_w8a8_linear_q8_allreduce",
     "asq_q8_linear_allreduce_nvls",
+    "asq_nvls_probe",
     "asq_dev_alloc",
     "asq_dev_free",
     "asq_ipc_export",
@@ -159,7 +160,9 @@ def load():
                                                      c_pp, c_pp, c_i, c_i, c_i, c_vp, c_vp]
         lib.asq_q8_linear_allreduce_nvls.restype = c_i
         lib.asq_q8_linear_allreduce_nvls.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_f,
-                                                     c_vp, c_pp, c_i, c_i, c_vp]
+                                                     c_vp, c_pp, c_vp, c_vp, c_sz, c_i, c_i, c_i, c_vp]
+        lib.asq_nvls_probe.restype = c_i
+        lib.asq_nvls_probe.argtypes = [c_vp, c_vp, c_sz, c_i, c_i, c_i, c_i, c_vp, c_vp]
         lib.asq_dev_alloc.restype = c_i
         lib.asq_dev_alloc.argtypes = [c_sz, c_pp]
         lib.asq_dev_free.restype = c_i

@@ -14,7 +14,8 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-SOURCES = [PKG_DIR / "csrc" / "asq_kernels.cu", PKG_DIR / "csrc" / "asq_glue.cu", PKG_DIR / "csrc" / "asq_smallm.cu"]
+SOURCES = [PKG_DIR / "csrc" / "asq_kernels.cu", PKG_DIR / "csrc" / "asq_glue.cu", PKG_DIR / "csrc" / "asq_smallm.cu",
+           PKG_DIR / "csrc" / "asq_nvls_probe.cu"]
 HEADERS = [PKG_DIR / "csrc" / "asq_ptx.cuh", PKG_DIR / "csrc" / "asq_smallm.h", REPO_ROOT / "include" / "asq.h"]
 # experiments: ASQ_LIB_NAME=libasq_b200_x.so ASQ_NVCC_DEFS="-DASQ_EPI_NBUF=1" builds (and _lib loads) a variant library
 LIB_PATH = PKG_DIR / os.environ.get("ASQ_LIB_NAME", "libasq_b200.so")
@@ -55,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         compile_flags += ["-Xptxas", "-v"]
     jobs = []
-    kernels_cu, glue_cu, smallm_cu = SOURCES
+    kernels_cu, glue_cu, smallm_cu, probe_cu = SOURCES
     with_mc = "-DASQ_ENABLE_MC" in compile_flags  # TUs 5 / 6: the 4-CTA multicast experiment (ASQ_MC=2), off by default
     for tu in range(N_KERNEL_TUS + 1):
         if tu in (5, 6) and not with_mc:
@@ -66,6 +67,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     jobs.append((obj, [nvcc, *compile_flags, "-o", str(obj), str(glue_cu)]))
     obj = OBJ_DIR / "asq_smallm.o"
     jobs.append((obj, [nvcc, *compile_flags, "-o", str(obj), str(smallm_cu)]))
+    obj = OBJ_DIR / "asq_nvls_probe.o"
+    jobs.append((obj, [nvcc, *compile_flags, "-o", str(obj), str(probe_cu)]))
     procs = [(obj, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for obj, cmd in jobs]
     logs = []
     for obj, cmd, proc in procs:

@@ -134,13 +134,23 @@ struct LinearParams {
   uint32_t* ar_ctl[8];
   uint32_t* ar_recv[8];
   // In-switch all-reduce (F_NVLS): every rank TMA-stores its 16-bit partial tiles into its OWN symmetric buffer (p.y)
-  // and bumps a counter on the tile's owner (rank tile % world, ar_ctl[owner]); the owner's epilogue warps then sum
-  // the world copies of their part of the tile with multimem.ld_reduce on the buffers' multicast address (the
-  // NVSwitch adds them, fp32 accumulation) and multimem.st the sums into every rank's output.  All ranks walk the
-  // tiles in the SAME order, so a tile's partials complete at about the same time everywhere and the reduction of
-  // tile i overlaps the main loop of tile i+1.
+  // and bumps a counter on the tile's owner (rank tile % world, ar_ctl[owner]).  A few reducer CTAs appended to the
+  // grid sum the world copies of the owned tiles with multimem.ld_reduce on the buffers' multicast address (the
+  // NVSwitch adds them) and multimem.st the sums into every rank's output.  All ranks walk the tiles in the SAME
+  // order, so a tile's partials complete at about the same time everywhere and the reduction of one round of tiles
+  // overlaps the MMAs of the next (see nvls_reducer_warp).
   const uint8_t* nvls_p_mc;  // multicast address of the partial buffers [M, N] 16-bit (NULL: not an NVLS launch)
   uint8_t* nvls_y_mc;        // multicast address of the outputs [M, N] 16-bit
+  int nvls_reducers;         // CTAs at the end of the grid that only reduce (see nvls_reducer_warp)
+  // "slab landed" counters, one per (tile, 64-row slab), in the same symmetric allocation: every rank bumps its LOCAL
+  // copy (a remote atomic per tile would wait behind the reduction traffic on the link: measured ~25 us each), the
+  // reducer reads the SUM over all ranks' copies with one multimem.ld_reduce.  Two banks alternate between launches;
+  // every launch clears the bank the next one will use (nobody reads it any more: the previous launch's handshake
+  // is complete) so no rank ever sees counts of an older launch.
+  uint32_t* nvls_ctr;            // this rank's copy of the current bank
+  const uint32_t* nvls_ctr_mc;   // multicast address of the current bank
+  uint32_t* nvls_ctr_next;       // this rank's copy of the other bank (cleared by this launch)
+  int nvls_ctr_words;            // words per bank in use by this launch's shape bound
   int tma_store;            // 1: outputs leave through shared-memory staging + TMA store (tmY is valid)
   unsigned long long* dbg;  // optional timeline buffer (8 slots per CTA), nullptr in production
 };
@@ -1007,54 +1017,80 @@ __device__ __forceinline__ uint4 multimem_ld_reduce_16(const void* mc_addr) {
                        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t multimem_ld_reduce_u32(const uint32_t* mc_addr) {
+  uint32_t v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u32 %0, [%1];" : "=r"(v) : "l"(mc_addr) : "memory");
+  return v;
+}
 template <bool BF>
 __device__ __forceinline__ void multimem_st_16(void* mc_addr, const uint4& v) {
   if (BF) asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
   else    asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One epilogue warp's part of an owned tile, remembered until its partials have arrived from every rank.
-struct NvlsPending {
-  int valid, row0, col0, ngroups, half;
-  uint32_t* counter;
-};
-
-// Sum this warp's part (32 rows x its 64-column groups) of an owned tile over all ranks and broadcast it.
-// `blocking` == false: return false at once if some rank's partial has not landed yet.
-template <bool BF>
-__device__ __forceinline__ bool nvls_reduce_part(const LinearParams& p, NvlsPending& pd, int lane, bool blocking) {
-  uint32_t seen = 0;
-  if (lane == 0) {
-    const uint32_t want = static_cast<uint32_t>(p.ar_world);
-    seen = ld_acquire_sys(pd.counter);
-    while (blocking && seen != want) { __nanosleep(64); seen = ld_acquire_sys(pd.counter); }
-    seen = (seen == want) ? 1u : 0u;
-  }
-  seen = __shfl_sync(0xffffffffu, seen, 0);
-  if (!seen) return false;
-  fence_acq_rel_sys();
+// Reducer CTAs of an NVLS launch (the last p.nvls_reducers CTAs of the grid; they compute no tiles).  The unit of work
+// is a 64-row slab of a tile this rank owns (t = rank + world * i): it has its own counter, bumped by the four
+// epilogue warps per rank that write it, and is reduced by ONE reducer warp — no CTA-wide synchronisation, so while
+// one warp waits for a slab to land the others keep streaming.  Slabs are dealt round-robin to all reducer warps in
+// walk order, i.e. in the order in which the GEMM CTAs of all ranks finish them.  A warp sums the world copies of
+// its slab in the switch (multimem.ld_reduce, NVLS_INFLIGHT 16-byte requests in flight per lane, a warp-wide
+// request covers 512 contiguous bytes of a row) and broadcasts the sums (multimem.st).  The GEMM CTAs never wait for
+// a reducer: the in-switch reduction of one round of tiles overlaps the MMAs of the next.
+constexpr int NVLS_INFLIGHT = 16;
+constexpr int NVLS_SLAB_ROWS = 64;
+template <bool BF, int CG>
+__device__ __forceinline__ void nvls_reducer_warp(const LinearParams& p, int rwarp, int num_rwarps, int lane) {
+  constexpr int SLABS = CG * BLOCK_M / NVLS_SLAB_ROWS;  // per tile
+  // timeline slots of a reducer CTA (its warp 0): 2 first slab landed, 3 first slab reduced, 4 ns spent waiting for
+  // counters, 5 ns spent reducing, 6 last slab reduced
+  const bool stamp = p.dbg != nullptr && (threadIdx.x == 0);
+  unsigned long long t_wait = 0, t_red = 0, t_a = 0, t_b = 0;
+  bool first = true;
+  const int owned = (p.ar_tiles - p.ar_rank + p.ar_world - 1) / p.ar_world;
+  const uint32_t target = static_cast<uint32_t>(p.ar_world) * 4u;  // 2 quadrants x 2 column halves per rank
   const int N = p.N;
-#pragma unroll 1
-  for (int g = pd.half; g < pd.ngroups; g += 2) {
-    const int col = pd.col0 + g * UNIT_N + (lane & 7) * 8;  // this lane's 16-byte piece of a 128-byte row segment
-    uint4 v[8];
-    bool ok[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = pd.row0 + i * 4 + (lane >> 3);
-      ok[i] = row < p.M && col < N;
-      if (ok[i]) v[i] = multimem_ld_reduce_16<BF>(p.nvls_p_mc + (static_cast<size_t>(row) * N + col) * 2);
+  for (int u = rwarp; u < owned * SLABS; u += num_rwarps) {
+    const int i = u / SLABS, slab = u - i * SLABS;
+    // the slab has landed everywhere when the SUM of all ranks' local counters reaches world x 4: one in-switch
+    // reduction per poll instead of one remote load per rank
+    const size_t ci = static_cast<size_t>(p.ar_rank + p.ar_world * i) * SLABS + slab;
+    if (stamp) t_a = globaltimer_ns();
+    if (lane == 0) {
+      // cheap local poll first (every rank runs the same schedule: when this rank's part has landed the others' are
+      // about to), then one switch round trip per poll
+      while (ld_acquire_gpu(p.nvls_ctr + ci) != 4u) __nanosleep(128);
+      while (multimem_ld_reduce_u32(p.nvls_ctr_mc + ci) != target) __nanosleep(256);
+      // The data requests below are issued only after this poll has returned (they are control-dependent on it) and
+      // are served by the switch from the ranks' L2s, never from a local cache, so a GPU-scope fence orders them; a
+      // system-scope fence here waits behind every multimem request this SM has in flight (measured ~20 us per slab).
+      __threadfence();
     }
+    __syncwarp();
+    if (stamp) { t_b = globaltimer_ns(); t_wait += t_b - t_a; if (first) ASQ_STAMP(2); }
+    int m_blk, n_blk;
+    tile_coords(p.ar_rank + p.ar_world * i, p, m_blk, n_blk);
+    const int row0 = m_blk * BLOCK_M * CG + slab * NVLS_SLAB_ROWS;
+    const int col0 = n_blk * p.tile_units * UNIT_N;
+    const int rows = min(NVLS_SLAB_ROWS, p.M - row0);
+    const int cpr = min(p.tile_units * UNIT_N, N - col0) / 8;  // 16-byte pieces per slab row (N % 8 == 0)
+    const int pieces = rows * cpr;                            // <= 0: the slab lies beyond M
+    for (int base = lane; base < pieces; base += 32 * NVLS_INFLIGHT) {
+      uint4 v[NVLS_INFLIGHT];
+      size_t off[NVLS_INFLIGHT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = pd.row0 + i * 4 + (lane >> 3);
-      if (ok[i]) multimem_st_16<BF>(p.nvls_y_mc + (static_cast<size_t>(row) * N + col) * 2, v[i]);
+      for (int k = 0; k < NVLS_INFLIGHT; ++k) {
+        const int c = base + k * 32;
+        const int r = c / cpr;
+        off[k] = (static_cast<size_t>(row0 + r) * N + col0 + (c - r * cpr) * 8) * 2;
+        if (c < pieces) v[k] = multimem_ld_reduce_16<BF>(p.nvls_p_mc + off[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < NVLS_INFLIGHT; ++k)
+        if (base + k * 32 < pieces) multimem_st_16<BF>(p.nvls_y_mc + off[k], v[k]);
     }
+    if (stamp) { t_red += globaltimer_ns() - t_b; if (first) ASQ_STAMP(3); first = false; }
   }
-  __syncwarp();
-  if (lane == 0) *pd.counter = 0u;  // re-arm: the peers' next increments come after this launch's end handshake
-  pd.valid = 0;
-  return true;
+  if (stamp) { p.dbg[blockIdx.x * 8 + 4] = t_wait; p.dbg[blockIdx.x * 8 + 5] = t_red; ASQ_STAMP(6); }
 }
 
 // Output maps of the other ranks' y buffers (all-reduce mode), in rank order skipping self.  Only the AR
@@ -1111,7 +1147,8 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t cluster_rank = (CG * MC > 1) ? cluster_ctarank() : 0u;
   const uint32_t cta_rank = cluster_rank & (CG - 1);              // 0 = leader of the pair
   const int pair_idx = static_cast<int>(cluster_rank) / CG;       // which pair of the cluster (MC == 2)
-  const int num_workers = gridDim.x / (CG * MC);                  // CTAs, CTA pairs or 4-CTA clusters
+  // CTAs, CTA pairs or 4-CTA clusters that compute tiles (an NVLS launch appends reducer CTAs, which compute none)
+  const int num_workers = (static_cast<int>(gridDim.x) - ((FEAT & F_NVLS) != 0 ? p.nvls_reducers : 0)) / (CG * MC);
   const int worker = blockIdx.x / (CG * MC);
   const bool fused = (FEAT & F_PHASE1) != 0 && (p.x != nullptr);
   if (threadIdx.x == 0) ASQ_STAMP(0);
@@ -1146,8 +1183,17 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) ASQ_STAMP(1);
+  if constexpr (kNVLS) {  // clear the counter bank of the NEXT launch (see LinearParams::nvls_ctr)
+    for (int i = blockIdx.x * NUM_THREADS + threadIdx.x; i < p.nvls_ctr_words; i += gridDim.x * NUM_THREADS) p.nvls_ctr_next[i] = 0u;
+  }
 
-  if (warp == 0) {
+  if (kNVLS && worker >= num_workers) {
+    // ===================== NVLS reducer CTA: in-switch sums of the tiles this rank owns =====================
+    const int rwarp = (static_cast<int>(blockIdx.x) - num_workers * CG) * (NUM_THREADS / 32) + warp;
+    const int num_rwarps = p.nvls_reducers * (NUM_THREADS / 32);
+    if (p.y_dtype == ASQ_BF16) nvls_reducer_warp<true, CG>(p, rwarp, num_rwarps, lane);
+    else                       nvls_reducer_warp<false, CG>(p, rwarp, num_rwarps, lane);
+  } else if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
       int stage = 0;
@@ -1293,8 +1339,6 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                (p.epi_kind == EPI_DEQUANT || p.epi_kind == EPI_SWIGLU);
     uint32_t gcount = 0;  // staging tiles issued by this warp (buffer = gcount & 1)
     uint32_t resid_phase = 0;  // parity of this warp's residual-tile barrier
-    NvlsPending nvls_pend;     // F_NVLS: this warp's part of the last owned tile, not yet reduced
-    nvls_pend.valid = 0;
     // all-reduce mode: this launch's epoch = 1 + the epoch of the last launch that finished on this rank
     const uint32_t ar_epoch = (AR && p.ar_world > 1) ? __ldcg(p.ar_ctl[p.ar_rank]) + 1u : 0u;
     int it = 0;
@@ -1692,32 +1736,20 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if constexpr (kNVLS) {
         // This warp's part of the tile's partial is on its way into this rank's buffer: once it has LANDED (bulk
-        // stores complete, not merely read from shared memory) tell the tile's owner.  The accumulator was already
-        // handed back above, so the next tile's MMAs run while this warp waits and reduces.
-        const int owner = sg.ar_tile % p.ar_world;
-        uint32_t* ctr = p.ar_ctl[owner] + AR_FLAG_BASE +
-                        (static_cast<size_t>(sg.ar_tile / p.ar_world) * CG + cta_rank) * NUM_EPI_WARPS + ew;
+        // stores complete, not merely read from shared memory) bump the tile's counter on its owner.  The accumulator
+        // was handed back above, so the next tile's MMAs are already running.
         if (lane == 0) {
+          const unsigned long long ts0 = (p.dbg != nullptr && ew == 0) ? globaltimer_ns() : 0ull;
           tma_store_wait_all();
           fence_proxy_async_all();  // async-proxy (TMA) writes before the generic-proxy release below
-          fence_acq_rel_sys();
-          red_release_sys_add(ctr, 1u);
+          // Release at GPU scope: the partial tile and the counter live in THIS GPU's memory, whose L2 is the point of
+          // coherence the switch reads through.  A system-scope fence here waits behind all multimem traffic the
+          // reducer CTAs have in flight: measured 22 us per tile (profiles/r02_allreduce.md), 30x the tile's math.
+          const int slab = static_cast<int>(cta_rank) * (BLOCK_M / NVLS_SLAB_ROWS) + (quad >> 1);
+          red_release_gpu_add(p.nvls_ctr + static_cast<size_t>(sg.ar_tile) * (CG * BLOCK_M / NVLS_SLAB_ROWS) + slab, 1u);
+          if (p.dbg != nullptr && ew == 0) p.dbg[blockIdx.x * 8 + 2] += globaltimer_ns() - ts0;  // ns spent signalling
         }
         __syncwarp();
-        const bool bf = (p.y_dtype == ASQ_BF16);
-        if (owner == p.ar_rank) {
-          // an owned tile: first finish the previous one (its partials had a whole tile time to arrive), then queue this one
-          if (nvls_pend.valid) { if (bf) nvls_reduce_part<true>(p, nvls_pend, lane, true); else nvls_reduce_part<false>(p, nvls_pend, lane, true); }
-          nvls_pend.valid = 1; nvls_pend.row0 = row0; nvls_pend.col0 = tile_col0; nvls_pend.ngroups = ngroups;
-          nvls_pend.half = half; nvls_pend.counter = ctr;
-        } else if (nvls_pend.valid) {
-          if (bf) nvls_reduce_part<true>(p, nvls_pend, lane, false); else nvls_reduce_part<false>(p, nvls_pend, lane, false);
-        }
-      }
-    }
-    if constexpr (kNVLS) {
-      if (nvls_pend.valid) {
-        if (p.y_dtype == ASQ_BF16) nvls_reduce_part<true>(p, nvls_pend, lane, true); else nvls_reduce_part<false>(p, nvls_pend, lane, true);
       }
     }
     if (lane == 0) tma_store_wait_all();  // staged tiles fully written before the CTA retires
@@ -1737,18 +1769,28 @@ asq_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // peer (their stores into OUR y and their reads of OUR partials are then complete) and advances the epoch.
     uint32_t* ctl = p.ar_ctl[p.ar_rank];
     const uint32_t epoch = __ldcg(ctl) + 1u;
-    __threadfence_system();
+    // stores into other ranks' memory (peer TMA stores / multimem.st) must be performed system-wide before this CTA
+    // counts as finished; the GEMM CTAs of an NVLS launch wrote local memory only
+    if (!kNVLS || worker >= num_workers) __threadfence_system();
+    else __threadfence();
+    if (kNVLS && worker >= num_workers) ASQ_STAMP(1);  // reducer CTA: its multimem stores are performed system-wide
     const uint32_t done = atomicAdd(ctl + 1, 1u);
     if (done == gridDim.x - 1) {
+      // timeline of the handshake (last CTA), slots of a virtual CTA after the grid: 0 entered, 1 peers told, 2 peers heard, 3 done
+      unsigned long long* hs = p.dbg != nullptr ? p.dbg + static_cast<size_t>(gridDim.x) * 8 : nullptr;
+      if (hs != nullptr) hs[0] = globaltimer_ns();
       ctl[1] = 0u;
       __threadfence_system();
       for (int r = 0; r < p.ar_world; ++r)
         if (r != p.ar_rank) st_release_sys(p.ar_ctl[r] + 2 + p.ar_rank, epoch);
+      if (hs != nullptr) hs[1] = globaltimer_ns();
       for (int r = 0; r < p.ar_world; ++r)
         if (r != p.ar_rank)
           while (ld_acquire_sys(ctl + 2 + r) != epoch) __nanosleep(200);
+      if (hs != nullptr) hs[2] = globaltimer_ns();
       ctl[0] = epoch;
       __threadfence_system();
+      if (hs != nullptr) hs[3] = globaltimer_ns();
     }
   }
   if (fused && threadIdx.x == 0) {
@@ -1935,6 +1977,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
                const asq::ExtraMapsT<asq::extra_kind(FEAT)>& tmPeers, const asq::LinearParams& p, int workers,
                cudaStream_t stream) {
   using Cfg = asq::TileCfg<CG>;
+  const int extra_ctas = (FEAT & asq::F_NVLS) != 0 ? p.nvls_reducers : 0;  // reducer CTAs appended to the grid
   auto kern = asq::asq_linear_kernel<FP8, CG, MC, FEAT>;
   cudaError_t e;
   {
@@ -1949,7 +1992,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG * MC), 1, 1);
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG * MC + extra_ctas), 1, 1);
   cfg.blockDim = dim3(asq::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -2166,7 +2209,16 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
       if (mc == 2) mc_clusters = clusters;
     }
   }
-  const int max_workers = (mc == 2) ? mc_clusters : st->sm_count / cg;
+  if (p.nvls_p_mc != nullptr) {
+    // reducer CTAs (ASQ_NVLS_REDUCERS, default 32): enough 16-byte requests in flight to keep the NVLink path busy
+    // (profiles/r02_allreduce.md: ~1 MB per GPU), taken from the SMs the GEMM would otherwise use
+    static int red_env = -1;
+    if (red_env < 0) { const char* e = getenv("ASQ_NVLS_REDUCERS"); red_env = (e != nullptr && atoi(e) > 0) ? atoi(e) : 0; }
+    int r = red_env ? red_env : 32;
+    if (r > st->sm_count / 2) r = st->sm_count / 2;
+    p.nvls_reducers = (r + cg - 1) / cg * cg;
+  }
+  const int max_workers = (mc == 2) ? mc_clusters : (st->sm_count - p.nvls_reducers) / cg;
   p.num_m_blocks = (p.M + tile_m - 1) / tile_m;
   p.tile_m_blocks = cg;
   p.n_units = (p.N + asq::UNIT_N - 1) / asq::UNIT_N;
@@ -2291,6 +2343,7 @@ int launch_linear(bool fp8, const void* a8, const void* w, asq::LinearParams& p,
     const bool out16n = (p.y_dtype == ASQ_BF16 || p.y_dtype == ASQ_F16);
     if (!p.tma_store || !out16n || p.epi_kind != asq::EPI_DEQUANT || p.x != nullptr || p.sk_enabled || mc != 1)
       return fail(ASQ_ERR_INVALID, "nvls all-reduce needs 8-bit activations and a 16-byte aligned 16-bit output row pitch");
+    p.ar_tiles = p.num_m_blocks * p.num_n_blocks;
     const asq::ExtraMapsT<0> none_nvls{};
     if (cg == 2) return fp8 ? launch_cfg<true, 2, 1, ASQ_LEAN_NVLS>(tmA, tmB, tmBu, tmY, none_nvls, p, workers, stream)
                             : launch_cfg<false, 2, 1, ASQ_LEAN_NVLS>(tmA, tmB, tmBu, tmY, none_nvls, p, workers, stream);
@@ -2811,9 +2864,18 @@ int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const
 int asq_q8_linear_allreduce_nvls(const void* xq, int fp8, const float* row_scale, const void* w, const float* bias,
                                  void* partial_local, const void* partial_mc, void* y_mc, int y_dtype, int64_t M,
                                  int64_t N, int64_t K, float dequant_scale, const float* col_scale,
-                                 void* const* ctl_all, int rank, int world, void* stream) {
+                                 void* const* ctl_all, void* counters_local, const void* counters_mc,
+                                 size_t counter_bank_bytes, int launch_parity, int rank, int world, void* stream) {
   if (world < 2 || world > 8 || rank < 0 || rank >= world || ctl_all == nullptr)
     return fail(ASQ_ERR_INVALID, "nvls allreduce: bad rank %d / world %d or null control table", rank, world);
+  if (counters_local == nullptr || counters_mc == nullptr || counter_bank_bytes % 16 != 0 || (launch_parity != 0 && launch_parity != 1))
+    return fail(ASQ_ERR_INVALID, "nvls allreduce: bad counter banks");
+  {
+    const int64_t slabs = ((M + asq::NVLS_SLAB_ROWS - 1) / asq::NVLS_SLAB_ROWS + 3) * ((N + asq::TILE_N - 1) / asq::TILE_N);
+    if (static_cast<size_t>(slabs) * 4 > counter_bank_bytes)
+      return fail(ASQ_ERR_WORKSPACE, "nvls allreduce: [%lld, %lld] needs %lld counter bytes per bank, got %zu", (long long)M, (long long)N,
+                  (long long)slabs * 4, counter_bank_bytes);
+  }
   for (int r = 0; r < world; ++r)
     if (ctl_all[r] == nullptr) return fail(ASQ_ERR_INVALID, "nvls allreduce: rank %d control buffer is null", r);
   if (partial_local == nullptr || partial_mc == nullptr || y_mc == nullptr || (reinterpret_cast<uintptr_t>(partial_mc) & 15) ||
@@ -2834,6 +2896,10 @@ int asq_q8_linear_allreduce_nvls(const void* xq, int fp8, const float* row_scale
   p.ar_world = world; p.ar_rank = rank;
   p.nvls_p_mc = static_cast<const uint8_t*>(partial_mc);
   p.nvls_y_mc = static_cast<uint8_t*>(y_mc);
+  p.nvls_ctr = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(counters_local) + launch_parity * counter_bank_bytes);
+  p.nvls_ctr_next = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(counters_local) + (1 - launch_parity) * counter_bank_bytes);
+  p.nvls_ctr_mc = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(counters_mc) + launch_parity * counter_bank_bytes);
+  p.nvls_ctr_words = static_cast<int>(counter_bank_bytes / 4);
   for (int r = 0; r < world; ++r) p.ar_ctl[r] = static_cast<uint32_t*>(ctl_all[r]);
   return launch_linear(fp8 != 0, xq, w, p, static_cast<cudaStream_t>(stream));
 }

@@ -89,9 +89,9 @@ def normalise_quant_config(cfg: Dict[str, str]) -> Dict[str, str]:
 
 
 def _rand_linear(in_f: int, out_f: int, gen: torch.Generator, device, std: float = 0.02) -> nn.Linear:
-    lin = nn.Linear(in_f, out_f, bias=False, device=device, dtype=torch.float32)
-    with torch.no_grad():
-        lin.weight.normal_(0.0, std, generator=gen)
+    lin = nn.Linear(in_f, out_f, bias=False, device="meta", dtype=torch.float32)  # no default init pass over the weight
+    lin.weight = nn.Parameter(torch.empty(out_f, in_f, dtype=torch.float32, device=device).normal_(0.0, std, generator=gen),
+                              requires_grad=False)
     return lin
 
 
@@ -102,7 +102,7 @@ def _make_proj(kind: str, in_f: int, out_f: int, qcfg: Dict[str, str], input_sca
     lin = _rand_linear(in_f, out_f, gen, device)
     gran = qcfg[kind]
     if qcfg["type"] == "fp8_e4m3":
-        mod = FP8LinearDynamic.from_float(lin, 1.0, act_quant="per-token", reference_compat=False)
+        mod = FP8LinearDynamic.from_float(lin, 1.0, save_device=device, act_quant="per-token", reference_compat=False)
     elif kind in ("qkv", "fc1"):
         mod = W8A8BFP32OFP32Linear.from_float(lin, input_scale, save_device=device, act_quant=gran)
     else:

@@ -64,7 +64,10 @@ class PeerComm:
                 # multimem.ld_reduce, the outputs for multimem.st
                 import torch.distributed._symmetric_memory as symm
 
-                self._nvls_tensor = symm.empty(3 * y_bytes, dtype=torch.uint8, device=self.device)
+                # + two banks of "slab landed" counters: 4 bytes per (64-row slab, 256-column tile), worst aspect ratio
+                slabs = ((self.max_m + 63) // 64 + 3) * ((self.max_n + 255) // 256) + 4 * ((self.max_m * self.max_n) // (64 * 256) + 64)
+                self._ctr_bank = (slabs * 4 + 1023) // 1024 * 1024
+                self._nvls_tensor = symm.empty(3 * y_bytes + 2 * self._ctr_bank, dtype=torch.uint8, device=self.device)
                 self._nvls_tensor.zero_()
                 pg = dist.group.WORLD if group is None else group
                 hdl = symm.rendezvous(self._nvls_tensor, pg.group_name)
@@ -73,7 +76,7 @@ class PeerComm:
                 self._nvls = hdl
                 self._nvls_mc = int(hdl.multicast_ptr)
                 self._nvls_local = int(self._nvls_tensor.data_ptr())
-                self._nvls_y_views = [self._nvls_tensor[y_bytes:2 * y_bytes], self._nvls_tensor[2 * y_bytes:]]
+                self._nvls_y_views = [self._nvls_tensor[y_bytes:2 * y_bytes], self._nvls_tensor[2 * y_bytes:3 * y_bytes]]
                 self._nvls_launches = 0
             if multicast:
                 # the output buffers live in torch symmetric memory so that an NVLS multicast address exists for them
@@ -198,7 +201,8 @@ class PeerComm:
             rc = lib.asq_q8_linear_allreduce_nvls(
                 xq.data_ptr(), 1 if fp8 else 0, _lib._ptr(row_scale), weight.data_ptr(), _lib._ptr(bias),
                 self._nvls_local, self._nvls_mc, self._nvls_mc + y_off, _lib._code(out_dtype), M, N, K, float(dequant_scale),
-                _lib._ptr(col_scale), self._tables["ctl"], self.rank, self.world, _lib._stream(self.device))
+                _lib._ptr(col_scale), self._tables["ctl"], self._nvls_local + 3 * self._y_bytes, self._nvls_mc + 3 * self._y_bytes,
+                self._ctr_bank, which, self.rank, self.world, _lib._stream(self.device))
         _lib._check(rc)
         _lib._launches += 1
         self._nvls_launches += 1

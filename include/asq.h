@@ -258,23 +258,38 @@ int asq_w8a8_linear_q8_allreduce(const int8_t* xq, const float* row_scale, const
 /* The same row-parallel linear with the sum taken INSIDE THE NVSWITCH (NVLS): the collective an NCCL NVLS
  * all-reduce performs, fused into the GEMM launch.  Every rank's epilogue TMA-stores its dequantised 16-bit
  * partial tiles (T(f * acc (+ bias)), the arithmetic of asq_w8a8_linear_q8) into its OWN slice of a symmetric
- * allocation and bumps a counter on the tile's owner (rank = tile % world); when a tile's counter reaches
- * `world`, the owner's epilogue warps read the tile through the allocation's multicast address with
- * multimem.ld_reduce (the switch adds the `world` copies, fp32 accumulation, one rounding to T) and write the
- * sums to every rank's output with multimem.st.  All ranks walk the tiles in the same order, so tile i's
- * reduction overlaps tile i+1's MMAs; nothing but 16-byte multimem traffic crosses NVLink.
+ * allocation and bumps a counter on the tile's owner (rank = tile % world); reducer CTAs appended to the same
+ * grid wait for the counters of the tiles their rank owns, read them through the allocation's multicast address
+ * with multimem.ld_reduce (the switch adds the `world` copies) and write the sums to every rank's output with
+ * multimem.st.  All ranks walk the tiles in the same order, so the reduction of one round of tiles overlaps the
+ * MMAs of the next; nothing but 16-byte multimem traffic crosses NVLink.  Measured on B200: the switch's 16-bit
+ * sum is within one ulp of the exactly rounded sum (not always equal to it), deterministic, identical on all ranks.
  *   xq [M, K/world], w [N, K/world]: int8 (fp8 == 0) or e4m3 (fp8 != 0: kind::f8f6f4, fp32 accumulate — the
  *       tensor-parallel FP8LinearDynamic of BASELINE config 5); row_scale = GLOBAL per-token scales or NULL
  *   bias on ONE rank only (it is part of that rank's partial), as for GEMM + ncclAllReduce
  *   partial_local: this rank's partial buffer [M, N] 16-bit; partial_mc / y_mc: multicast addresses of all
  *       ranks' partial / output buffers (cuMulticast* or torch symmetric memory, same offset on every rank)
- *   ctl_all [world]: the control buffers of asq_ar_buffer_bytes (own + asq_ipc_open'ed), zero-filled once
+ *   ctl_all [world]: the control buffers of asq_ar_buffer_bytes (own + asq_ipc_open'ed), zero-filled once (they
+ *       carry only the end-of-launch handshake here)
+ *   counters_local / counters_mc: this rank's copy and the multicast address of 2 x counter_bank_bytes of "slab
+ *       landed" counters in the same symmetric allocation, zero-filled once; a rank bumps only its LOCAL copy, a
+ *       reducer reads the sum over all ranks with one multimem.ld_reduce; launch_parity (0 / 1, alternating per
+ *       launch on this group) selects the bank, the other bank is cleared for the next launch.  A bank needs
+ *       4 bytes per (64-row slab, 256-column tile) of the largest [M, N].
  * Numerics: those of asq_w8a8_linear_q8 followed by an NVLS ncclAllReduce in T.  Every rank must issue the
  * same sequence of calls; a launch returns only after every peer has finished writing this rank's output. */
 int asq_q8_linear_allreduce_nvls(const void* xq, int fp8, const float* row_scale, const void* w, const float* bias,
                                  void* partial_local, const void* partial_mc, void* y_mc, int y_dtype, int64_t M,
                                  int64_t N, int64_t K, float dequant_scale, const float* col_scale,
-                                 void* const* ctl_all, int rank, int world, void* stream);
+                                 void* const* ctl_all, void* counters_local, const void* counters_mc,
+                                 size_t counter_bank_bytes, int launch_parity, int rank, int world, void* stream);
+
+/* Measurement aid, not on the product path: drives the NVLS data path with the access pattern of the kernel above
+ * (16-byte multimem.ld_reduce / multimem.st, `unroll` requests in flight per thread, ctas x threads threads) over
+ * `bytes` bytes of two multicast-mapped buffers.  mode 0: dst = sum over ranks of src, 1: ld_reduce only, 2:
+ * multimem.st only.  Gives the measured ceiling the collective half of the fused kernel is reported against. */
+int asq_nvls_probe(const void* src_mc, void* dst_mc, size_t bytes, int ctas, int threads, int unroll, int mode,
+                   void* sink, void* stream);
 
 /* Zero-filled cudaMalloc memory and CUDA IPC handles (64 bytes) to map it into the other ranks' processes. */
 int asq_dev_alloc(size_t bytes, void** ptr);

@@ -33,6 +33,7 @@ def timeit(fn, iters=20, warmup=3):
 
 
 Mmax = 2048 * world
+nvls_only = "nvls-only" in sys.argv
 comm = peer.PeerComm(device=dev, max_m=Mmax, max_n=4096)
 comm_mc = peer.PeerComm(device=dev, max_m=Mmax, max_n=4096, multicast=True)
 comm_nv = peer.PeerComm(device=dev, max_m=Mmax, max_n=4096, nvls=True, p2p=False)
@@ -46,6 +47,11 @@ for (M, N, K) in [(2048, 4096, 4096), (2048, 4096, 11008), (Mmax, 4096, 4096), (
         dist.all_reduce(y)
         return y
 
+    if nvls_only:
+        t_nv = timeit(lambda: comm_nv.linear_q8_allreduce_nvls(a, w, None, 1e-4))
+        if rank == 0:
+            print(f"world {world}  {M}x{N}x{K} (K/rank {Kl}): fused NVLS (in-switch) {t_nv:6.1f} us  [ASQ_NVLS_REDUCERS={os.environ.get('ASQ_NVLS_REDUCERS', 'default')}]", flush=True)
+        continue
     t_gemm = timeit(lambda: L.w8a8_linear_q8(a, w, None, 1e-4))
     y = L.w8a8_linear_q8(a, w, None, 1e-4)
     t_ar = timeit(lambda: dist.all_reduce(y))

