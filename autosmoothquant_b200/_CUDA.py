@@ -36,11 +36,20 @@ class I8CUGEMM:
     def linear_a8_w8_o8_(self, input: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, alpha: float,
                          beta: float = 0.0) -> None:
         """out (int8) = sat(rint(alpha * (input @ weight^T) + beta * out_in))  (bindings.cpp:104-121).
-        With beta == 0 (the default and the only value the reference's callers use) ``out`` is write-only."""
-        if beta != 0.0:
-            raise NotImplementedError("linear_a8_w8_o8_ with beta != 0 (full [M,N] addend) is outside the W8A8 path; "
-                                      "use linear_a8_w8_b8_o8_ for a per-column bias")
-        _lib.i8gemm_epi(input, weight, out, alpha, 0.0)
+        With beta == 0 (the default and the only value the reference's callers use) ``out`` is write-only and the call
+        is one fused launch.  beta != 0 reads the previous contents of ``out`` as the cuBLASLt C operand
+        (cublasINT8MMWrapper.cc:537-672): the GEMM launch emits fp32 ``alpha * acc`` and one elementwise pass applies
+        ``+ beta * out_in``, rint and saturation — the same fp32 operations in the same order as the fused alpha / beta
+        epilogue of ``linear_a8_w8_b8_o8_``, on an entry point nothing in the reference calls."""
+        if beta == 0.0:
+            _lib.i8gemm_epi(input, weight, out, alpha, 0.0)
+            return
+        if out.dtype != torch.int8 or tuple(out.shape) != (input.shape[0], weight.shape[0]):
+            raise ValueError("linear_a8_w8_o8_: out must be int8 [M,N]")
+        scaled = torch.empty(out.shape, dtype=torch.float32, device=out.device)
+        _lib.i8gemm_epi(input, weight, scaled, alpha, 0.0)
+        out.copy_(torch.clamp(torch.round(scaled + torch.tensor(beta, dtype=torch.float32, device=out.device) * out.to(torch.float32)),
+                              -128, 127).to(torch.int8))
 
     def linear_a8_w8_b8_o8_(self, input: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, alpha: float,
                             beta: float) -> torch.Tensor:

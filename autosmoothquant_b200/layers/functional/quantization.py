@@ -58,3 +58,29 @@ def per_token_quantize_fp8(tensor: torch.Tensor) -> Tuple[torch.Tensor, torch.Te
 def static_per_tensor_quantize_fp8(tensor: torch.Tensor, inv_scale) -> torch.Tensor:
     """e4m3(clamp(tensor / inv_scale)) (quantization.py:208-211)."""
     return (tensor / inv_scale).clamp(min=-E4M3_MAX, max=E4M3_MAX).to(torch.float8_e4m3fn)
+
+
+def dtype_byte_size(dtype: torch.dtype) -> float:
+    """Bytes per element of `dtype`, float8 types included.  The reference monkeypatches
+    ``transformers.modeling_utils.dtype_byte_size`` with a regex-based version (quantization.py:126-136) because the
+    transformers release it pins mis-sizes ``torch.float8_e4m3fn`` when ``save_pretrained`` shards an FP8 checkpoint;
+    this one asks torch (``bool`` counts as one bit, as in transformers)."""
+    if dtype == torch.bool:
+        return 1 / 8
+    if not isinstance(dtype, torch.dtype):
+        raise ValueError(f"`dtype` is not a valid dtype: {dtype}.")
+    return torch.empty((), dtype=dtype).element_size()
+
+
+def install_dtype_byte_size_patch() -> bool:
+    """Same side effect as importing the reference's quantization module: transformers' checkpoint sharding sizes FP8
+    tensors correctly.  Returns False when transformers is not importable (nothing to patch)."""
+    try:
+        import transformers.modeling_utils as mu
+    except Exception:  # noqa: BLE001
+        return False
+    mu.dtype_byte_size = dtype_byte_size
+    return True
+
+
+install_dtype_byte_size_patch()

@@ -274,11 +274,22 @@ class _FP8Base(nn.Module):
             self.register_buffer(name, torch.tensor(1.0, dtype=torch.float32, requires_grad=False))
 
     def _apply(self, fn, *args, **kwargs):
+        """Device moves apply to everything; DTYPE moves (``.half()``, ``.to(torch.bfloat16)``) must not touch what the
+        kernel consumes: float8 counts as floating point, so ``module.half()`` would otherwise turn the e4m3 weight into
+        fp16 (the reference's dequantise-and-F.linear path tolerates that, a tensor-core FP8 GEMM cannot).  The weight
+        is brought back to e4m3 (lossless: its values are e4m3 values), the bias is widened to fp32 once, the scalar
+        scales return to the host as fp32 (reference :405-409, 542-548)."""
         super()._apply(fn, *args, **kwargs)
+        w = getattr(self, "weight", None)
+        if w is not None and w.dtype not in (torch.float8_e4m3fn, torch.uint8) and w.is_floating_point():
+            self.weight = w.to(torch.float8_e4m3fn)
+        b = getattr(self, "bias", None)
+        if self.use_bias and b is not None and b.dtype != torch.float32:
+            self.bias = b.to(torch.float32)
         for name in self._scale_names:
             buf = getattr(self, name, None)
-            if buf is not None and buf.device.type != "cpu":
-                setattr(self, name, buf.cpu())
+            if buf is not None and (buf.device.type != "cpu" or buf.dtype != torch.float32):
+                setattr(self, name, buf.to(torch.float32).cpu())
         return self
 
     def _bias_f32(self) -> Optional[torch.Tensor]:
@@ -389,8 +400,10 @@ class FP8StaticLinearQuantizer(nn.Module):
 
 
 class FP8E5M2Linear(nn.Module):
-    """e5m2 weights, unscaled ``torch._scaled_mm`` (reference :584-644).  Not part of any benchmarked
-    configuration; kept as the same thin library call the reference makes."""
+    """e5m2 weights and e5m2-rounded activations, no scales (reference :584-644).  Not part of any benchmarked
+    configuration.  The reference calls ``torch._scaled_mm`` on two e5m2 operands, a combination cuBLASLt rejects on
+    current stacks; the same product is evaluated here as a plain torch matmul of the e5m2-rounded operands widened
+    to the activation dtype (fp32 accumulation inside the library GEMM), which is what that call would return."""
 
     def __init__(self, in_features, out_features, use_bias=False):
         super().__init__()
@@ -403,10 +416,8 @@ class FP8E5M2Linear(nn.Module):
             self.register_buffer("bias", torch.empty(out_features, dtype=torch.float32, requires_grad=False))
 
     def forward(self, x):
-        one = torch.ones((), dtype=torch.float32, device=x.device)
-        x2 = x.reshape(-1, self.in_features).to(torch.float8_e5m2)
-        out = torch._scaled_mm(x2, self.weight.t(), scale_a=one, scale_b=one,
-                               bias=self.bias.to(x.dtype) if self.use_bias else None, out_dtype=x.dtype)
+        x2 = x.reshape(-1, self.in_features).to(torch.float8_e5m2).to(x.dtype)
+        out = torch.nn.functional.linear(x2, self.weight.to(x.dtype), self.bias.to(x.dtype) if self.use_bias else None)
         return out.view(*x.shape[:-1], self.out_features)
 
     @staticmethod

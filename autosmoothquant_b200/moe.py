@@ -86,7 +86,9 @@ def route_tokens(selected_experts: torch.Tensor, num_experts: int):
     flat = selected_experts.reshape(-1)
     n = flat.numel()
     m_pad = (n + num_experts * (SEGMENT_ALIGN - 1)) // SEGMENT_ALIGN * SEGMENT_ALIGN
-    counts = torch.bincount(flat, minlength=num_experts)
+    # one-hot sum instead of torch.bincount: bincount sizes its output from the data (a host synchronisation, and an
+    # error under CUDA-graph capture); this form has a static shape
+    counts = F.one_hot(flat, num_classes=num_experts).sum(dim=0)
     padded = (counts + SEGMENT_ALIGN - 1) // SEGMENT_ALIGN * SEGMENT_ALIGN
     seg_end = torch.cumsum(padded, 0)
     seg_start = seg_end - padded

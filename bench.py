@@ -75,6 +75,7 @@ def parse_args():
                          "fused / fused-int32 = GEMM fused with NVLink peer stores (16-bit / exact int32 partials), "
                          "nccl = GEMM launch + ncclAllReduce; auto = nvls when the system has NVLS multicast, else nccl")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="capture a CUDA graph even for the sparse-MoE stack (default there: eager)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip module_path / dp_replicas / reference_native_gpu")
     ap.add_argument("--no-parity", action="store_true", help="skip the tp_parity gate (debugging only)")
@@ -562,6 +563,8 @@ def run_ours(args, cfg, layers):
         print(json.dumps({"profiled_step": True, "launches_per_step": launches_per_step}))
         return
     graph = None
+    if moe and not args.graph:
+        args.no_graph = True  # routing is data dependent torch code around the two grouped launches: eager by default
     if not args.no_graph:
         try:
             graph, static_ids, static_out = capture_graph(model, ids_dev, logits)

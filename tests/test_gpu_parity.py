@@ -156,6 +156,11 @@ def test_i8gemm_epi_variants():
     got = g.linear_a8_w8_b8_o8_(t(a), t(w), t(bias8), float(alpha), float(beta))
     want = O.sat_i8(np.rint(alpha * acc + beta * bias8.astype(np.float32)))
     np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # beta != 0 on the in-place variant: the previous contents of `out` are the addend (bindings.cpp:104-121)
+    c0 = rng.integers(-128, 128, size=(M, N), dtype=np.int8)
+    out2 = t(c0).clone()
+    g.linear_a8_w8_o8_(t(a), t(w), out2, float(alpha), float(beta))
+    np.testing.assert_array_equal(out2.cpu().numpy(), O.sat_i8(np.rint(alpha * acc + beta * c0.astype(np.float32))))
     outf = torch.empty((M, N), dtype=torch.float32, device=DEV)
     biasf = rng.standard_normal(N).astype(np.float32)
     L.i8gemm_epi(t(a), t(w), outf, float(alpha), float(beta), bias=t(biasf), relu=True)

@@ -104,3 +104,25 @@ def test_quant_config_semantics():
     with pytest.raises(ValueError):
         harness.normalise_quant_config({"type": "int4"})
     assert harness.LLAMA2_7B.linear_macs_per_token_per_layer() == 4 * 4096 ** 2 + 3 * 4096 * 11008
+
+
+def test_fp8_modules_survive_dtype_moves():
+    """module.half() / .to(bfloat16) must leave the e4m3 weight, the fp32 bias and the host-side fp32 scales intact
+    (float8 is a floating-point dtype to nn.Module._apply); FP8E5M2Linear runs as a plain torch product."""
+    import torch
+    from autosmoothquant_b200.layers.nn.linear import FP8E5M2Linear, FP8LinearDynamic, FP8LinearStatic
+
+    lin = torch.nn.Linear(32, 16, bias=True)
+    for mod in (FP8LinearDynamic.from_float(lin, reference_compat=False), FP8LinearStatic(32, 16, True)):
+        w0 = mod.weight.view(torch.uint8).clone()
+        for move in (lambda m: m.half(), lambda m: m.to(torch.bfloat16), lambda m: m.float()):
+            mod = move(mod)
+            assert mod.weight.dtype == torch.float8_e4m3fn and torch.equal(mod.weight.view(torch.uint8), w0)
+            assert mod.bias.dtype == torch.float32
+            for name in mod._scale_names:
+                buf = getattr(mod, name)
+                assert buf.dtype == torch.float32 and buf.device.type == "cpu" and buf.dim() == 0
+    e5 = FP8E5M2Linear.from_float(lin)
+    x = torch.randn(3, 32)
+    want = torch.nn.functional.linear(x.to(torch.float8_e5m2).float(), lin.weight.data.to(torch.float8_e5m2).float(), lin.bias.data)
+    assert torch.allclose(e5(x), want, atol=1e-5)
