@@ -113,7 +113,9 @@ def test_fp8_modules_survive_dtype_moves():
     from autosmoothquant_b200.layers.nn.linear import FP8E5M2Linear, FP8LinearDynamic, FP8LinearStatic
 
     lin = torch.nn.Linear(32, 16, bias=True)
-    for mod in (FP8LinearDynamic.from_float(lin, reference_compat=False), FP8LinearStatic(32, 16, True)):
+    static = FP8LinearStatic(32, 16, True)
+    static.weight = lin.weight.data.to(torch.float8_e4m3fn)  # torch.empty() storage may hold NaN codes, whose sign a 16-bit trip loses
+    for mod in (FP8LinearDynamic.from_float(lin, reference_compat=False), static):
         w0 = mod.weight.view(torch.uint8).clone()
         for move in (lambda m: m.half(), lambda m: m.to(torch.bfloat16), lambda m: m.float()):
             mod = move(mod)
