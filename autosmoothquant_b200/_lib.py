@@ -219,8 +219,43 @@ def _code(dtype: torch.dtype) -> int:
         raise TypeError(f"unsupported dtype {dtype}") from None
 
 
+# ---------------------------------------------------------------- launch ordering across streams
+# asq_linear_kernel is a persistent grid of one CTA (pair) per SM whose CTAs wait on each other inside the launch
+# (phase-1 panel counters, the grid-wide absmax, stream-K partials, all-reduce flags).  That is live as long as every
+# CTA of the grid eventually becomes resident: true next to any FINITE foreign kernel (NCCL, attention, copies — they
+# drain and free their SMs), but NOT next to a second grid of the same kind on another stream: each could hold part of
+# the SMs and spin on CTAs of its own that can never be scheduled.  So launches of one device are kept stream-ordered:
+# when a launch arrives on a different stream than the previous one, the new stream first waits (event) for everything
+# queued on the old one.  Launches on one stream — the normal case, and everything replayed from one CUDA graph — pay
+# a dictionary look-up.  ASQ_STREAM_GUARD=0 removes the check (callers that order their streams themselves).  Users of
+# the C ABI own this rule: see INTEGRATION.md, "Streams".
+_STREAM_GUARD = os.environ.get("ASQ_STREAM_GUARD", "1") != "0"
+_last_launch_stream: dict = {}  # device index -> torch.cuda.Stream that carried the most recent launch
+
+
+def _order_after_previous_launch(dev: torch.device, cur) -> None:
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    prev = _last_launch_stream.get(idx)
+    if prev is not None and prev.cuda_stream == cur.cuda_stream:
+        return
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture: ordering against streams outside the capture is the capturing code's business
+        # (torch.cuda.graph already makes the capture stream wait for the caller's stream), and an event from an
+        # uncaptured stream would invalidate the capture.  The captured launches are ordered among themselves.
+        return
+    if prev is not None:
+        try:
+            cur.wait_stream(prev)
+        except RuntimeError:
+            pass  # `prev` is being captured by another thread: nothing of it runs now, nothing to wait for
+    _last_launch_stream[idx] = cur
+
+
 def _stream(dev: torch.device) -> int:
-    return torch.cuda.current_stream(dev).cuda_stream
+    cur = torch.cuda.current_stream(dev)
+    if _STREAM_GUARD:
+        _order_after_previous_launch(dev, cur)
+    return cur.cuda_stream
 
 
 # ---------------------------------------------------------------- workspace

@@ -86,5 +86,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+CEILING_SRC = PKG_DIR / "csrc" / "asq_ceiling.cu"
+CEILING_LIB = PKG_DIR / "libasq_ceiling.so"
+
+
+def build_ceiling(force: bool = False) -> Path:
+    """The tcgen05 issue-rate microbenchmark (csrc/asq_ceiling.cu -> libasq_ceiling.so): a measurement utility with
+    its own library, so the drop-in library of include/asq.h is not touched by it (scripts/int8_ceiling.py, bench.py)."""
+    deps = [CEILING_SRC, PKG_DIR / "csrc" / "asq_ptx.cuh"]
+    if not force and CEILING_LIB.exists() and all(p.stat().st_mtime <= CEILING_LIB.stat().st_mtime for p in deps):
+        return CEILING_LIB
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(CEILING_LIB), str(CEILING_SRC)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    return CEILING_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_ceiling(force=True))

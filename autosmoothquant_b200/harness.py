@@ -411,12 +411,33 @@ def _moe_half_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Optional
     return x2, layer._moe_forward(h)
 
 
+_NVTX = os.environ.get("ASQ_NVTX", "0") == "1"  # named ranges per decoder-block half for timeline tools (off: zero cost)
+
+
+class _Range:
+    """`with _Range("layer3.attn"):` -> an NVTX range when ASQ_NVTX=1 (host-side markers only: legal under graph capture)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _layer_forward_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Optional[torch.Tensor], B: int, S: int,
-                        rope: RopeTables):
-    x2, delta = _attention_half_glue(layer, x2, delta, B, S, rope)
-    if layer.moe is not None:
-        return _moe_half_glue(layer, x2, delta)
-    return _mlp_half_glue(layer, x2, delta)
+                        rope: RopeTables, index: int = 0):
+    with _Range(f"asq.layer{index}.attention"):
+        x2, delta = _attention_half_glue(layer, x2, delta, B, S, rope)
+    with _Range(f"asq.layer{index}.mlp"):
+        if layer.moe is not None:
+            return _moe_half_glue(layer, x2, delta)
+        return _mlp_half_glue(layer, x2, delta)
 
 
 class QuantDecoder(nn.Module):
@@ -471,8 +492,8 @@ class QuantDecoder(nn.Module):
             from . import _lib
 
             x2, delta = x.view(B * S, -1), None
-            for layer in self.layers:
-                x2, delta = _layer_forward_glue(layer, x2, delta, B, S, rope)
+            for i, layer in enumerate(self.layers):
+                x2, delta = _layer_forward_glue(layer, x2, delta, B, S, rope, i)
             if last_token_only:  # only the last position of every sequence feeds the lm_head
                 x2 = x2.view(B, S, -1)[:, -1, :].contiguous()
                 delta = delta.view(B, S, -1)[:, -1, :].contiguous() if delta is not None else None

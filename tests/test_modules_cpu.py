@@ -128,3 +128,36 @@ def test_fp8_modules_survive_dtype_moves():
     x = torch.randn(3, 32)
     want = torch.nn.functional.linear(x.to(torch.float8_e5m2).float(), lin.weight.data.to(torch.float8_e5m2).float(), lin.bias.data)
     assert torch.allclose(e5(x), want, atol=1e-5)
+
+
+def test_launches_are_kept_stream_ordered(monkeypatch):
+    """Two persistent grids must never share the SMs (their CTAs wait on each other): when a launch arrives on another
+    stream than the previous one, the new stream waits for the old one first; inside a CUDA-graph capture nothing is
+    recorded.  Exercised with stand-in stream objects (no GPU here)."""
+    import torch
+    from autosmoothquant_b200 import _lib
+
+    class FakeStream:
+        def __init__(self, handle):
+            self.cuda_stream, self.waited = handle, []
+
+        def wait_stream(self, other):
+            self.waited.append(other.cuda_stream)
+
+    a, b, cap = FakeStream(11), FakeStream(22), FakeStream(33)
+    state = {"cur": a, "capturing": False}
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: state["cur"])
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: state["capturing"])
+    monkeypatch.setattr(_lib, "_last_launch_stream", {})
+    dev = torch.device("cuda", 0)
+    assert _lib._stream(dev) == 11 and _lib._stream(dev) == 11 and a.waited == []  # same stream: nothing to do
+    state["cur"] = b
+    assert _lib._stream(dev) == 22 and b.waited == [11]  # b waits for everything queued on a
+    assert _lib._stream(dev) == 22 and b.waited == [11]
+    state.update(cur=cap, capturing=True)
+    assert _lib._stream(dev) == 33 and cap.waited == []  # capture: no cross-stream event, bookkeeping untouched
+    state.update(cur=a, capturing=False)
+    assert _lib._stream(dev) == 11 and a.waited == [22]
+    monkeypatch.setattr(_lib, "_STREAM_GUARD", False)
+    state["cur"] = b
+    assert _lib._stream(dev) == 22 and b.waited == [11]  # guard off: no new wait

@@ -115,3 +115,61 @@ def test_fused_module_equals_reference_path_on_gpu(ref_gemm, cls, act, dtype):
     torch.cuda.synchronize()
     assert y.dtype == want.dtype and y.shape == want.shape
     assert torch.equal(y, want), f"max |diff| {(y.float() - want.float()).abs().max().item()}"
+
+
+BASELINE_SHAPES = [  # Llama-2-7B prefill launches of BASELINE configs[1] (M = 2048 tokens): (K, N, class, granularity)
+    (4096, 4096, "W8A8BFP32OFP32Linear", "per-tensor"),                  # q_proj
+    (4096, 11008, "W8A8BFP32OFP32Linear", "per-tensor"),                 # gate_proj / up_proj
+    (4096, 4096, "W8A8BFP32OFP32LinearWithQuantScale", "per-tensor"),    # o_proj
+    (11008, 4096, "W8A8BFP32OFP32LinearWithQuantScale", "per-tensor"),   # down_proj
+    (11008, 4096, "W8A8BFP32OFP32LinearWithQuantScale", "per-token"),    # down_proj, BASELINE config 3 granularity
+]
+
+
+@pytest.mark.parametrize("K,N,cls,act", BASELINE_SHAPES)
+def test_fused_module_equals_reference_path_at_baseline_sizes(ref_gemm, K, N, cls, act):
+    """The FUSED OUTPUT (not only the int32 GEMM) at the sizes the metric is quoted on: one launch of ours against the
+    reference's eager prologue + its own cuBLASLt GEMM + eager epilogue, bf16, every element bit-equal."""
+    g = torch.Generator(device=DEV).manual_seed(K + N)
+    M = 2048
+    lin = torch.nn.Linear(K, N, bias=True, device=DEV)
+    with torch.no_grad():
+        lin.weight.normal_(0.0, 0.02, generator=g)
+        lin.bias.normal_(0.0, 1.0, generator=g)
+    mod = getattr(NN, cls).from_float(lin, 0.04, save_device=DEV, act_quant=act).to(DEV)
+    del lin
+    scale = 30.0 if cls == "W8A8BFP32OFP32Linear" else 1.0
+    x = (torch.randn(1, M, K, device=DEV, generator=g) * scale).to(torch.bfloat16)
+    x[0, 5, :] = 0.25  # a flat row: every element ties at the same code
+    y = mod(x)
+    qs = float(mod.quant_scale) if (hasattr(mod, "quant_scale") and act == "per-tensor") else None
+    want = need(reference_forward(ref_gemm, x, mod.weight, mod.dequant_scale, mod.bias, act, qs))
+    torch.cuda.synchronize()
+    assert y.dtype == want.dtype and y.shape == want.shape == (1, M, N)
+    assert torch.equal(y, want), f"max |diff| {(y.float() - want.float()).abs().max().item()}"
+    # and the codes the GEMM consumed are not degenerate: the per-tensor cases saturate some and use the whole range
+    assert int(mod.weight.abs().max()) == 127
+
+
+def test_fused_qkv_module_equals_reference_path_at_baseline_size(ref_gemm):
+    """W8A8BFP32OFP32QKVLinear.forward (linear.py:172-208) at 2048 x 12288 x 4096: one int32 GEMM over the packed
+    weight, every third dequantised with its own scale, concatenated — against our single launch with a column-scale vector."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    M, K, H = 2048, 4096, 4096
+    lin = torch.nn.Linear(K, 3 * H, bias=True, device=DEV)
+    with torch.no_grad():
+        lin.weight.normal_(0.0, 0.02, generator=g)
+        lin.weight[H:2 * H] *= 3.0  # the three blocks get visibly different weight scales
+        lin.bias.normal_(0.0, 1.0, generator=g)
+    mod = NN.W8A8BFP32OFP32QKVLinear.from_float(lin, 0.04, [H, H, H], save_device=DEV, act_quant="per-tensor").to(DEV)
+    del lin
+    x = (torch.randn(M, K, device=DEV, generator=g) * 30.0).to(torch.bfloat16)
+    y = mod(x)
+    q = x.round().clamp(-128, 127).to(torch.int8)
+    acc = need(ref_o32(ref_gemm, q, mod.weight))
+    scales = [float(mod.q_dequant_scale), float(mod.k_dequant_scale), float(mod.v_dequant_scale)]
+    assert len({round(s, 12) for s in scales}) == 3
+    parts = [s * a for s, a in zip(scales, acc.split([H, H, H], dim=-1))]
+    want = (torch.cat(parts, dim=-1) + mod.bias).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(y, want), f"max |diff| {(y.float() - want.float()).abs().max().item()}"
