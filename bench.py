@@ -783,7 +783,7 @@ def run_ours(args, cfg, layers):
         ceil_tops = (ceiling or {}).get("best", {}).get("fp8" if fp8 else "i8")
         # the denominator SURVEY 8(d) asks for: the measured tcgen05 issue rate of this operand type (held to a
         # plausibility window so that a broken measurement cannot flatter or void the line); else 2 x measured bf16
-        if ceil_tops and 1500.0 <= ceil_tops <= 4700.0:
+        if ceil_tops and 1500.0 <= ceil_tops <= 5000.0:
             peak = ceil_tops
             peak_src = (f"tcgen05 kind::{'f8f6f4' if fp8 else 'i8'} issue-rate microbenchmark (csrc/asq_ceiling.cu, {ceil_src}): "
                         "resident smem operands, the kernel's MMA shape, every SM busy")
