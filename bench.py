@@ -797,11 +797,16 @@ def run_ours(args, cfg, layers):
         assert config["global_batch"] == B * replicas and config["parallelism"] == par_label
         details = {
             "cuda_graph": used_graph,
-            "projections": ("q|k|v and gate|up fused per layer (4 GEMM launches/layer)" if getattr(model, "glue", False) or not args.no_fuse
-                            else "one launch per projection (7 launches/layer)"),
-            "glue": ("RMSNorm->int8 producer kernel (asq_glue.cu); RoPE in the q|k|v epilogue; SiLU(gate)*up and down_proj's "
-                     "quantisation in the gate|up epilogue; residual adds in the o_proj / down_proj epilogues (1 GPU); "
-                     "o_proj quantises in-kernel")
+            "projections": (("q|k|v fused; all experts of a block in two grouped launches (w1|w3 + SwiGLU, w2): 4 GEMM launches/layer" if moe
+                             else "q|k|v and gate|up fused per layer (4 GEMM launches/layer)")
+                            if getattr(model, "glue", False) or not args.no_fuse else "one launch per projection (7 launches/layer)"),
+            "glue": (("RMSNorm->int8 producer kernel (asq_glue.cu); RoPE in the q|k|v epilogue; o_proj quantises in-kernel (+ residual "
+                      "epilogue on 1 GPU); router softmax / top-k / scatter in torch (eager, no CUDA graph); SiLU(w1 x)*(w3 x) in the "
+                      "grouped w1|w3 epilogue; w2 quantises per token in-kernel")
+                     if moe else
+                     ("RMSNorm->int8 producer kernel (asq_glue.cu); RoPE in the q|k|v epilogue; SiLU(gate)*up and down_proj's "
+                      "quantisation in the gate|up epilogue; residual adds in the o_proj / down_proj epilogues (1 GPU); "
+                      "o_proj quantises in-kernel"))
                     if getattr(model, "glue", False)
                     else "torch norms / RoPE / SiLU; every linear quantises its own input in-kernel",
             "wall_s_timed_region": t_wall,
