@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = (
     "asq_workspace_bytes",
     "asq_w8a8_linear",
     "asq_fp8_linear",
+    "asq_fp8_linear_cs",
     "asq_i8gemm_o32",
     "asq_i8gemm_epi",
     "asq_quantize_act",
@@ -122,6 +123,9 @@ def load():
         lib.asq_fp8_linear.restype = c_i
         lib.asq_fp8_linear.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_f, c_f, c_f,
                                        c_vp, c_i, c_vp, c_sz, c_vp]
+        lib.asq_fp8_linear_cs.restype = c_i
+        lib.asq_fp8_linear_cs.argtypes = [c_vp, c_i, c_vp, c_vp, c_vp, c_i, c_i64, c_i64, c_i64, c_i, c_vp,
+                                          c_vp, c_i, c_vp, c_sz, c_vp]
         lib.asq_i8gemm_o32.restype = c_i
         lib.asq_i8gemm_o32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_sz, c_vp]
         lib.asq_i8gemm_epi.restype = c_i
@@ -353,10 +357,13 @@ def fp8_linear(
     row_scale_out: Optional[torch.Tensor] = None,
     div_mode: Optional[int] = None,
     out_scale: float = 0.0,
+    col_scale: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Fused quantise -> e4m3 GEMM (fp32 accumulate) -> scale (+bias); ``weight`` is float8_e4m3fn [N,K]."""
+    """Fused quantise -> e4m3 GEMM (fp32 accumulate) -> scale (+bias); ``weight`` is float8_e4m3fn [N,K].
+    col_scale [N] fp32 (device) replaces the scalar ``w_scale`` by one weight scale per output column (horizontally
+    fused projections: asq_fp8_linear_cs); dynamic activation modes only."""
     global _launches
-    dev = _require_cuda(x, weight, bias, row_scale_out)
+    dev = _require_cuda(x, weight, bias, row_scale_out, col_scale)
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
         raise ValueError(f"shape mismatch: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
     if weight.dtype not in (torch.float8_e4m3fn, torch.uint8):
@@ -378,11 +385,22 @@ def fp8_linear(
         stream = _stream(dev)
         need = lib.asq_workspace_bytes(M, K)
         ws, ws_bytes = _workspace(dev, stream, need)
-        rc = lib.asq_fp8_linear(
-            x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
-            M, N, K, act_mode, float(in_scale), float(w_scale), float(out_scale), _ptr(row_scale_out),
-            _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
-        )
+        if col_scale is not None:
+            if col_scale.dtype != torch.float32 or col_scale.numel() != N or not col_scale.is_contiguous():
+                raise ValueError("col_scale must be a contiguous float32 [N] tensor")
+            if out_scale != 0.0 or act_mode == ACT_SCALE:
+                raise ValueError("col_scale: dynamic activation scales only, no output fake-quantisation")
+            rc = lib.asq_fp8_linear_cs(
+                x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
+                M, N, K, act_mode, col_scale.data_ptr(), _ptr(row_scale_out),
+                _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
+            )
+        else:
+            rc = lib.asq_fp8_linear(
+                x.data_ptr(), _code(x.dtype), weight.data_ptr(), _ptr(bias), y.data_ptr(), _code(out_dtype),
+                M, N, K, act_mode, float(in_scale), float(w_scale), float(out_scale), _ptr(row_scale_out),
+                _default_div_mode if div_mode is None else div_mode, ws, ws_bytes, stream,
+            )
     _check(rc)
     _launches += 1
     return y

@@ -2554,6 +2554,17 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
                       row_scale_out, div_mode, workspace, workspace_bytes, stream, out_scale);
 }
 
+int asq_fp8_linear_cs(const void* x, int x_dtype, const uint8_t* w_e4m3, const float* bias, void* y, int y_dtype,
+                      int64_t M, int64_t N, int64_t K, int act_mode, const float* w_col_scale, float* row_scale_out,
+                      int div_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (w_col_scale == nullptr) return fail(ASQ_ERR_INVALID, "asq_fp8_linear_cs needs the [N] column scales");
+  if (act_mode != ASQ_ACT_PER_TOKEN && act_mode != ASQ_ACT_PER_TENSOR_DYNAMIC && act_mode != ASQ_ACT_ROW_SCALE_GIVEN)
+    return fail(ASQ_ERR_UNSUPPORTED, "asq_fp8_linear_cs: dynamic activation scales only (act_mode %d)", act_mode);
+  // the epilogue multiplies by col_scale[n] * s[m]: the scalar dequant scale is unused when a column vector is given
+  return fused_linear(true, x, x_dtype, w_e4m3, bias, y, y_dtype, M, N, K, act_mode, 1.0f, 1.0f, w_col_scale,
+                      row_scale_out, div_mode, workspace, workspace_bytes, stream, 0.f);
+}
+
 // ---- RMSNorm as the prologue of the q|k|v and gate|up launches (the norm kernel disappears from the layer)
 namespace {
 int prep_rmsnorm_prologue(asq::LinearParams& p, const void* x, int x_dtype, const void* norm_weight, float eps, int64_t M,

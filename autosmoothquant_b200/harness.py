@@ -133,6 +133,39 @@ def _fuse_columns(mods, device) -> W8A8BFP32OFP32QKVLinear:
     return fused.to(device)
 
 
+class FP8FusedColumnsLinear(nn.Module):
+    """FP8LinearDynamic per-token projections that share their input (q|k|v, gate|up) as ONE launch: e4m3 weights
+    concatenated along N, every block keeps its own per-tensor weight scale as a per-output-column vector
+    (`asq_fp8_linear_cs`) — the FP8 counterpart of the reference's fused-W_pack INT8 module (linear.py:132-245).  The
+    activation is quantised once instead of once per projection; every output element goes through the same arithmetic
+    as in the separate launches, so the result is bit-identical to running the projections one by one."""
+
+    def __init__(self, mods):
+        super().__init__()
+        if not mods or any(not isinstance(m, FP8LinearDynamic) or m.act_quant != "per-token" for m in mods):
+            raise ValueError("FP8FusedColumnsLinear fuses per-token FP8LinearDynamic modules")
+        if len({m.in_features for m in mods}) != 1 or len({m.use_bias for m in mods}) != 1:
+            raise ValueError("fused projections must share in_features and all have (or all lack) a bias")
+        self.in_features = mods[0].in_features
+        self.sizes = [m.out_features for m in mods]
+        self.out_features = sum(self.sizes)
+        self.use_bias = mods[0].use_bias
+        dev = mods[0].weight.device
+        self.register_buffer("weight", torch.cat([m.weight.view(torch.uint8) for m in mods], dim=0).contiguous().view(torch.float8_e4m3fn))
+        self.register_buffer("col_scale", torch.cat([torch.full((m.out_features,), float(m.weight_scale), dtype=torch.float32)
+                                                     for m in mods]).to(dev))
+        if self.use_bias:
+            self.register_buffer("bias", torch.cat([m.bias.to(torch.float32) for m in mods]).contiguous())
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+
+        x2 = x.reshape(-1, self.in_features)
+        y = _lib.fp8_linear(x2, self.weight, self.bias if self.use_bias else None, _lib.ACT_PER_TOKEN, col_scale=self.col_scale)
+        return y.view(*x.shape[:-1], self.out_features)
+
+
 def rms_norm_hf(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     """HF LlamaRMSNorm.forward (what the reference's QuantizedLlamaRMSNorm inherits, models/llama.py:27-37):
     normalise in fp32, round to the activation dtype, then multiply by the (folded) weight."""
@@ -206,6 +239,14 @@ class QuantDecoderLayer(nn.Module):
             if self.moe is None:
                 self.gate_up_proj = _fuse_columns([self.gate_proj, self.up_proj], device)
                 del self.gate_proj, self.up_proj
+            self.fused = True
+        elif fuse_projections and self.moe is None and os.environ.get("ASQ_FP8_FUSE", "1") != "0":
+            # FP8 per-token (BASELINE config 5): 7 -> 4 launches per layer, the [M, hidden] input quantised twice instead
+            # of five times; under tensor parallelism this matters most for the narrow k / v shards (N = 128 at 70B / TP8)
+            self.qkv_sizes = [self.q_proj.out_features, self.k_proj.out_features, self.v_proj.out_features]
+            self.qkv_proj = FP8FusedColumnsLinear([self.q_proj, self.k_proj, self.v_proj])
+            self.gate_up_proj = FP8FusedColumnsLinear([self.gate_proj, self.up_proj])
+            del self.q_proj, self.k_proj, self.v_proj, self.gate_proj, self.up_proj
             self.fused = True
 
     def enable_swiglu_epilogue(self) -> None:

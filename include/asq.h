@@ -142,6 +142,17 @@ int asq_fp8_linear(const void* x, int x_dtype, const uint8_t* w_e4m3, const floa
                    float* row_scale_out, int div_mode,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* asq_fp8_linear with one dequantisation scale per OUTPUT COLUMN: w_col_scale [N] fp32 on the device replaces the
+ * scalar w_scale, y = T( acc * (w_col_scale[n] * s_x[m]) (+ bias) ).  Horizontally fused FP8 projections that share
+ * their input (q|k|v, gate|up: weights concatenated along N, the activation quantised once) keep the per-tensor
+ * weight scale of each block — the FP8 counterpart of W8A8BFP32OFP32QKVLinear (linear.py:132-245, 197-200).
+ * Dynamic activation scales only: ASQ_ACT_PER_TOKEN, ASQ_ACT_PER_TENSOR_DYNAMIC, ASQ_ACT_ROW_SCALE_GIVEN. */
+int asq_fp8_linear_cs(const void* x, int x_dtype, const uint8_t* w_e4m3, const float* bias,
+                      void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                      int act_mode, const float* w_col_scale,
+                      float* row_scale_out, int div_mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same GEMM + dequant epilogue for activations that are ALREADY int8 (emitted by a fused producer such as
  * asq_add_rmsnorm_quant / asq_silu_mul_quant): no prologue runs.  row_scale [M] fp32 or NULL supplies
  * per-token scales for the epilogue. */

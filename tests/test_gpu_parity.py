@@ -764,6 +764,45 @@ def test_config5_shapes_fp8_per_token(name, M, N, K):
     assert err <= want.abs().max().item() * (2 ** -8 + K * 2 ** -24), name
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_fp8_fused_columns_equal_separate_launches(dtype, use_bias):
+    """q|k|v (and gate|up) FP8 per-token projections as ONE launch with a per-column weight-scale vector
+    (asq_fp8_linear_cs, harness.FP8FusedColumnsLinear) == the three module forwards, bit for bit: every output element
+    sees the same codes, the same fp32 accumulation and the same factor fl(w_scale * s[m])."""
+    from autosmoothquant_b200.harness import FP8FusedColumnsLinear
+
+    g = torch.Generator().manual_seed(3)
+    M, K = 300, 512
+    mods = []
+    for n, std in ((256, 0.02), (128, 0.3), (136, 1.5)):  # three clearly different weight scales; 136: a ragged N tail
+        lin = torch.nn.Linear(K, n, bias=use_bias)
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(n, K, generator=g) * std)
+            if use_bias:
+                lin.bias.copy_(torch.randn(n, generator=g))
+        mods.append(NN.FP8LinearDynamic.from_float(lin, act_quant="per-token", reference_compat=False)._apply(lambda t: t.to(DEV)))
+    assert len({float(m.weight_scale) for m in mods}) == 3
+    fused = FP8FusedColumnsLinear(mods)
+    x = torch.randn(2, M // 2, K, generator=g)
+    x[0, 3, :] = 0.0  # an all-zero token: scale 0
+    x[1, 7, 5] = 3e4
+    x = x.to(dtype).to(DEV)
+    before = L.launch_count()
+    y = fused(x)
+    assert L.launch_count() - before == 1
+    want = torch.cat([m(x) for m in mods], dim=-1)
+    torch.cuda.synchronize()
+    assert y.dtype == dtype and y.shape == want.shape == (2, M // 2, 520)
+    assert torch.equal(y.view(torch.int32 if dtype == torch.float32 else torch.int16),
+                       want.view(torch.int32 if dtype == torch.float32 else torch.int16))  # bit patterns: NaN-safe (zero token)
+    # the column vector is validated: static scales and wrong lengths are rejected before any launch
+    with pytest.raises(ValueError):
+        L.fp8_linear(x.view(-1, K), fused.weight, None, L.ACT_PER_TOKEN, col_scale=fused.col_scale[:-1].contiguous())
+    with pytest.raises(ValueError):
+        L.fp8_linear(x.view(-1, K), fused.weight, None, L.ACT_SCALE, 0.5, col_scale=fused.col_scale)
+
+
 # ----------------------------------------------------------------------------- batched INT8 GEMM (csrc/kernels/bmm.cu)
 @pytest.mark.parametrize("B,M,N,K", [(4, 256, 192, 128), (3, 512, 512, 64), (5, 100, 72, 48), (1, 300, 64, 32), (32, 256, 256, 128)])
 def test_i8bmm_family_vs_exact_integer_matmul(B, M, N, K):

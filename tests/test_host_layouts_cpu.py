@@ -55,3 +55,23 @@ def test_quant_config_normalisation():
         except ValueError:
             continue
         raise AssertionError(f"{bad} accepted")
+
+
+def test_fp8_fused_columns_layout_cpu():
+    """harness.FP8FusedColumnsLinear: e4m3 bytes concatenated along N, one weight scale per output column, fp32 bias."""
+    from autosmoothquant_b200.layers.nn.linear import FP8LinearDynamic
+
+    torch.manual_seed(0)
+    mods = [FP8LinearDynamic.from_float(torch.nn.Linear(32, n, bias=True), act_quant="per-token", reference_compat=False)
+            for n in (16, 8, 8)]
+    fused = harness.FP8FusedColumnsLinear(mods)
+    assert fused.sizes == [16, 8, 8] and fused.out_features == 32 and fused.weight.dtype == torch.float8_e4m3fn
+    assert torch.equal(fused.weight.view(torch.uint8)[16:24], mods[1].weight.view(torch.uint8))
+    assert fused.col_scale.dtype == torch.float32 and fused.col_scale.shape == (32,)
+    assert torch.equal(fused.col_scale[24:], torch.full((8,), float(mods[2].weight_scale)))
+    assert fused.bias.dtype == torch.float32 and torch.equal(fused.bias[:16], mods[0].bias)
+    import pytest
+    with pytest.raises(ValueError):  # per-tensor-dynamic modules (the converter's quirk product) are not fusable
+        harness.FP8FusedColumnsLinear([FP8LinearDynamic.from_float(torch.nn.Linear(32, 8))])
+    with pytest.raises(RuntimeError):  # and there is no CPU fallback for the forward
+        fused(torch.randn(4, 32))
