@@ -380,8 +380,12 @@ def _attention_half_glue(layer: "QuantDecoderLayer", x2: torch.Tensor, delta: Op
     if o_tp is not None:
         # row-parallel wrapper: quantise (global row scales when per-token), GEMM, all-reduce (tp.RowParallelLinear)
         return x2, o_tp(attn2)
-    if os.environ.get("ASQ_OPROJ_SPLIT") == "1" and om.act_quant == "per-tensor":
-        # experiment: stand-alone quantisation kernel + int8-in GEMM instead of the in-kernel prologue
+    if os.environ.get("ASQ_OPROJ_SPLIT", "1") != "0" and om.act_quant == "per-tensor":
+        # per-tensor o_proj: a stand-alone quantisation kernel + the int8-in GEMM instead of the in-kernel prologue.  The
+        # attention output comes from a library kernel, so no producer can emit it as int8; inside the GEMM launch the
+        # prologue is exposed before the first MMA of a 1.73-round problem (50.7 us), as its own ~5 us launch it is not:
+        # 38.0 us for the GEMM, 12.74 vs 13.17 ms per Llama-2-7B step (profiles/r02/ab_oproj_split.md).  Bit-identical
+        # (the same row routine quantises in both).  ASQ_OPROJ_SPLIT=0 restores the single launch.
         q8o, _ = _lib.quantize_act(attn2, _lib.ACT_SCALE, float(om.quant_scale.item()))
         y = _lib.w8a8_linear_q8(q8o, om.weight, om.bias if om.use_bias else None, float(om.dequant_scale.item()),
                                 out_dtype=x2.dtype, residual=x2 if fuse_res else None)

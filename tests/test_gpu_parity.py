@@ -607,6 +607,7 @@ def test_glue_stack_norm_prologue_is_bit_identical(monkeypatch):
     ids = torch.randint(0, harness.TINY.vocab, (2, 96), generator=torch.Generator().manual_seed(4)).to(DEV)
     for qc in ({}, {"out": "per-token", "fc2": "per-token"}):
         model = harness.QuantDecoder(harness.TINY, qc, device=DEV, seed=5, fuse_projections=True, glue=True)
+        monkeypatch.setenv("ASQ_OPROJ_SPLIT", "0")  # count the one-launch-per-GEMM form (the default quantises o_proj's input in its own launch)
         monkeypatch.setenv("ASQ_NORM_PROLOGUE", "0")
         want = model(ids, last_token_only=False)
         monkeypatch.setenv("ASQ_NORM_PROLOGUE", "1")
