@@ -370,6 +370,68 @@ class ClockSampler(threading.Thread):
         return out
 
 
+# ----------------------------------------------------------------------------- per-launch timing of one eager step
+def make_launch_timers(events, event_factory, max_routed_rows):
+    """Wrappers that bracket every launch on the quantized-linear path with a pair of events on the launching stream and
+    append (start, end, algorithmic ops, (entry, M, N, K), is_collective) to `events`.
+    timed(fn, label, collective): a GEMM entry point of `_lib` (x, weight, ...) or a PeerComm method (self, x, weight, ...);
+    timed_prologue(fn): a stand-alone activation-quantisation launch (x, ...): 0 ops, its time counts."""
+
+    def timed(fn, label, collective=False):
+        def wrapper(*a, **kw):
+            x = a[1] if collective else a[0]
+            weight = a[2] if collective else a[1]
+            s, e = event_factory(), event_factory()
+            s.record()
+            out = fn(*a, **kw)
+            e.record()
+            n, rows = weight.shape[0], x.shape[0]
+            if label == "w8a8_grouped_linear":  # stacked expert weights [G*N, K]; x holds the routed slots + padding rows
+                n = weight.shape[0] // a[3].numel()
+                rows = min(rows, max_routed_rows)
+            events.append((s, e, 2.0 * rows * x.shape[1] * n, (label, rows, n, x.shape[1]), collective))
+            return out
+        return wrapper
+
+    def timed_prologue(fn):
+        def wrapper(x, *a, **kw):
+            s, e = event_factory(), event_factory()
+            s.record()
+            out = fn(x, *a, **kw)
+            e.record()
+            events.append((s, e, 0.0, ("quantize_act (stand-alone prologue launch)", x.shape[0], 0, x.shape[1]), False))
+            return out
+        return wrapper
+
+    return timed, timed_prologue
+
+
+def aggregate_launch_events(events):
+    """Sums over the launches of one step: the quantized-linear launches (stand-alone prologue launches included: 0 ops, their
+    time counts), the launches fused with a collective, and the per-(entry, shape) break-down."""
+    out = {"lin_time": 0.0, "lin_ops": 0.0, "n_lin": 0, "coll_time": 0.0, "coll_ops": 0.0, "coll_bytes": 0.0, "n_coll": 0}
+    by_shape = {}
+    for s, e, ops, key, collective in events:
+        dt = s.elapsed_time(e) * 1e-3
+        if collective:
+            out["coll_time"] += dt
+            out["coll_ops"] += ops
+            out["coll_bytes"] += key[1] * key[2] * 2.0  # the 16-bit [M, N] message the launch all-reduces
+            out["n_coll"] += 1
+        else:
+            out["lin_time"] += dt
+            out["lin_ops"] += ops
+            out["n_lin"] += 1
+        agg = by_shape.setdefault(key, [0, 0.0, 0.0])
+        agg[0] += 1
+        agg[1] += dt
+        agg[2] += ops
+    out["by_launch_shape"] = [{"entry": k[0], "M": k[1], "N": k[2], "K": k[3], "launches": v[0],
+                               "avg_us": v[1] / v[0] * 1e6, "tops": (v[2] / v[1] / 1e12) if v[1] > 0 else 0.0}
+                              for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])]
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def _physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -638,33 +700,7 @@ def run_ours(args, cfg, layers):
 
     events = []
 
-    def timed(fn, label, collective=False):
-        def wrapper(*a, **kw):
-            x = a[1] if collective else a[0]
-            weight = a[2] if collective else a[1]
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = fn(*a, **kw)
-            e.record()
-            n, rows = weight.shape[0], x.shape[0]
-            if label == "w8a8_grouped_linear":  # stacked expert weights [G*N, K]; x holds the routed slots + padding rows
-                n = weight.shape[0] // a[3].numel()
-                rows = min(rows, B * S * cfg.top_k)
-            events.append((s, e, 2.0 * rows * x.shape[1] * n, (label, rows, n, x.shape[1]), collective))
-            return out
-        return wrapper
-
-    def timed_prologue(fn):
-        """A stand-alone activation-quantisation launch that feeds a quantized linear (o_proj's input, row-parallel inputs,
-        tensor-parallel per-token scales): its time is charged to the linears, it adds no algorithmic ops."""
-        def wrapper(x, *a, **kw):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = fn(x, *a, **kw)
-            e.record()
-            events.append((s, e, 0.0, ("quantize_act (stand-alone prologue launch)", x.shape[0], 0, x.shape[1]), False))
-            return out
-        return wrapper
+    timed, timed_prologue = make_launch_timers(events, lambda: torch.cuda.Event(enable_timing=True), B * S * cfg.top_k)
 
     lib_names = ("w8a8_linear", "w8a8_linear_q8", "fp8_linear", "w8a8_gateup_swiglu", "w8a8_grouped_linear", "i8gemm_o32")
     originals = {name: getattr(_lib, name) for name in lib_names}
@@ -708,26 +744,9 @@ def run_ours(args, cfg, layers):
         _lib.quantize_act = orig_quantize_act
         if world > 1:
             dist.all_reduce = orig_all_reduce
-    lin_time = lin_ops = 0.0
-    n_lin = 0
-    coll_time = coll_ops = coll_bytes = 0.0
-    n_coll = 0
-    by_shape = {}
-    for s, e, ops, key, collective in events:
-        dt = s.elapsed_time(e) * 1e-3
-        if collective:
-            coll_time += dt
-            coll_ops += ops
-            coll_bytes += key[1] * key[2] * 2.0
-            n_coll += 1
-        else:
-            lin_time += dt
-            lin_ops += ops
-            n_lin += 1
-        agg = by_shape.setdefault(key, [0, 0.0, 0.0])
-        agg[0] += 1
-        agg[1] += dt
-        agg[2] += ops
+    agg = aggregate_launch_events(events)
+    lin_time, lin_ops, n_lin = agg["lin_time"], agg["lin_ops"], agg["n_lin"]
+    coll_time, coll_bytes, n_coll = agg["coll_time"], agg["coll_bytes"], agg["n_coll"]
     nccl_time = sum(s.elapsed_time(e) * 1e-3 for s, e, _ in nccl_events)
     nccl_bytes = float(sum(b for _, _, b in nccl_events))
 
@@ -853,9 +872,7 @@ def run_ours(args, cfg, layers):
                 "per_rank": tp,
                 "launches_timed_note": "every launch on the quantized-linear path of a step, stand-alone activation-quantisation "
                                        "launches included (0 ops, their time counts)",
-                "by_launch_shape": [{"entry": k[0], "M": k[1], "N": k[2], "K": k[3], "launches": v[0],
-                                     "avg_us": v[1] / v[0] * 1e6, "tops": v[2] / v[1] / 1e12}
-                                    for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])],
+                "by_launch_shape": agg["by_launch_shape"],
             },
         }
         if tp:
