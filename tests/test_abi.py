@@ -59,6 +59,13 @@ def test_argument_validation_happens_before_any_device_work(lib):
     assert b"multiple of 16" in lib.asq_last_error()
     rc = lib.asq_quantize_act(None, 7, None, None, 4, 32, 0, ctypes.c_float(1.0), 0, 0, None)  # bad dtype
     assert rc == -1
+    # asq_fp8_linear_cs: the column-scale vector is mandatory, static activation scales are not a mode of it
+    buf = (ctypes.c_char * 4096)()
+    addr = (ctypes.addressof(buf) + 1023) & ~1023
+    args = [addr, 2, addr, None, addr, 2, 4, 16, 32]
+    assert lib.asq_fp8_linear_cs(*args, 2, None, None, 0, None, 0, None) == -1 and b"column scales" in lib.asq_last_error()
+    rc = lib.asq_fp8_linear_cs(*args, 1, addr, None, 0, None, 0, None)  # ASQ_ACT_SCALE
+    assert rc == -2 and b"dynamic activation scales only" in lib.asq_last_error()  # ASQ_ERR_UNSUPPORTED
 
 
 def test_fails_loudly_without_a_device(lib):
