@@ -443,6 +443,9 @@ def _physical_gpu_index(local_rank):
     return local_rank
 
 
+NVLS_MEASURED_WORLDS = frozenset({2, 8})  # world sizes at which the fused GEMM + all-reduce kernels ran in round 2
+
+
 def pick_tp_reduce(args, world, dev, fp8):
     """auto: at 2 GPUs the GEMM fused with NVLink peer stores (a switch reduction sends the local copy over the link
     too: measured slower there, profiles/r02_allreduce.md); beyond, the GEMM fused with the in-switch all-reduce when
@@ -451,6 +454,10 @@ def pick_tp_reduce(args, world, dev, fp8):
         return args.tp_reduce, None
     if world == 2 and not fp8:
         return "fused", None
+    if world not in NVLS_MEASURED_WORLDS:
+        # the in-switch kernel is world-generic but has only RUN at these world sizes (profiles/r02_allreduce.md); an
+        # unattended benchmark does not take a first run of a cross-GPU spin-wait protocol: --tp-reduce nvls opts in
+        return "nccl", f"auto picks the in-switch kernel only where it has been measured (world {sorted(NVLS_MEASURED_WORLDS)}); NCCL at world {world}"
     import torch
     import torch.distributed as dist
 
@@ -492,7 +499,9 @@ def tp_parity_gate(args, cfg, dev, world, rank, fp8, moe):
     scale = float(want.abs().max())
     modes = []
     if not fp8 and not moe:
-        modes += [("nccl-int32", True), ("fused-int32", True)]
+        modes += [("nccl-int32", True)]
+        if world in NVLS_MEASURED_WORLDS or args.tp_reduce in ("fused", "fused-int32"):
+            modes += [("fused-int32", True)]  # peer-store kernel: exercised this round at these world sizes only
     timed = args.tp_reduce
     if timed not in [m for m, _ in modes]:
         modes.append((timed, False))

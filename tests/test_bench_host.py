@@ -116,3 +116,15 @@ def test_reference_arm_prints_the_contract_line():
     q = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference"], capture_output=True, text=True, timeout=120,
                        env={**__import__("os").environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert q.returncode == 0 and q.stdout.strip() == ""
+
+
+def test_auto_reduction_policy(bench):
+    """auto: peer stores at 2 GPUs, the in-switch kernel only at world sizes where it has run (8; at 2 FP8 has no other fused
+    option and probes for a multicast address), NCCL elsewhere; an explicit choice is never overridden."""
+    auto = SimpleNamespace(tp_reduce="auto")
+    assert bench.pick_tp_reduce(auto, 2, None, False) == ("fused", None)
+    mode, note = bench.pick_tp_reduce(auto, 4, None, False)
+    assert mode == "nccl" and "world 4" in note
+    assert bench.pick_tp_reduce(auto, 4, None, True)[0] == "nccl"
+    for explicit in ("nccl", "nccl-int32", "fused", "fused-int32", "nvls"):
+        assert bench.pick_tp_reduce(SimpleNamespace(tp_reduce=explicit), 4, None, False) == (explicit, None)
