@@ -75,3 +75,39 @@ def test_fp8_fused_columns_layout_cpu():
         harness.FP8FusedColumnsLinear([FP8LinearDynamic.from_float(torch.nn.Linear(32, 8))])
     with pytest.raises(RuntimeError):  # and there is no CPU fallback for the forward
         fused(torch.randn(4, 32))
+
+
+def test_route_tokens_properties_hypothesis():
+    """Property test of the expert-sorted, 256-row padded layout (the grouped kernel's contract): every routed slot gets
+    its own row inside its expert's segment, segments are 256-aligned and ordered by expert, slots keep their original
+    order inside a segment (stable), unused 128-row blocks are marked -1, and the worst-case bound holds — for any expert
+    count, top-k and routing, including experts with no tokens and a single token."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 3), st.integers(1, 300), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def check(E, k, T, seed, skewed):
+        g = torch.Generator().manual_seed(seed)
+        if skewed:  # most tokens to one expert, some experts empty
+            sel = torch.where(torch.rand(T, k, generator=g) < 0.85, torch.zeros(T, k, dtype=torch.int64),
+                              torch.randint(0, E, (T, k), generator=g))
+        else:
+            sel = torch.randint(0, E, (T, k), generator=g)
+        dest, blk, m_pad = moe.route_tokens(sel, E)
+        flat = sel.reshape(-1)
+        n = flat.numel()
+        assert m_pad % 256 == 0 and m_pad >= n and m_pad <= n + E * 255 and blk.numel() == m_pad // 128
+        assert dest.shape == (n,) and dest.unique().numel() == n and int(dest.min()) >= 0 and int(dest.max()) < m_pad
+        assert torch.equal(blk[dest // 128].long(), flat)  # every slot sits in a block of its own expert
+        counts = torch.bincount(flat, minlength=E)
+        padded = (counts + 255) // 256 * 256
+        starts = torch.cumsum(padded, 0) - padded
+        for e in range(E):
+            rows = dest[flat == e]
+            assert torch.equal(rows, starts[e] + torch.arange(int(counts[e])))  # contiguous from the segment start, stable
+        used = int(padded.sum()) // 128
+        assert (blk[used:] == -1).all() and (blk[:used] >= 0).all()
+        real = blk[:used]
+        assert torch.equal(real, torch.sort(real)[0])  # segments ordered by expert
+
+    check()
