@@ -104,3 +104,47 @@ def test_opt125m_calibrate_smooth_quantize_on_cpu(opt125m):
         w_scale = float(ds) / layer_scales[0][key]
         ref_w = smoothed["model.decoder.layers.0." + proj]
         assert float((w.float() * w_scale - ref_w).abs().max()) <= 0.5 * w_scale * 1.001
+
+
+def test_hf_llama_calibrate_smooth_quantize_save_on_cpu(tmp_path):
+    """The same chain on the INSTALLED transformers' LlamaForCausalLM (random-init, small): the pipeline finds HF's decoder
+    layers by structure, the static scales carry the reference's names (collect_llama_layer_scales), per-tensor qkv / fc1
+    fold their input scale into the RMSNorm weights, out / fc2 stay per-token (BASELINE config 3's granularities), and the
+    saved directory is the reference's on-disk pair with its state-dict keys."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from autosmoothquant_b200.layers.nn.linear import W8A8BFP32OFP32Linear, W8A8BFP32OFP32LinearWithQuantScale
+    from autosmoothquant_b200.quantize import load_quantized, save_quantized
+
+    cfg = LlamaConfig(vocab_size=320, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, max_position_embeddings=128)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    batches = [torch.randint(0, 320, (1, 48), generator=g) for _ in range(4)]
+    with torch.no_grad():
+        before = model(batches[0]).logits
+    act_scales = get_act_scales(model, batches)
+    assert "model.layers.1.mlp.down_proj" in act_scales and act_scales["model.layers.0.self_attn.q_proj"].shape == (64,)
+    assert smooth_lm(model, act_scales, alpha=0.5) == 2
+    with torch.no_grad():
+        after = model(batches[0]).logits
+    assert float((after - before).abs().max()) <= 2e-3 * float(before.abs().max())  # an exact re-parametrisation
+    layer_scales, _ = get_static_decoder_layer_scales(model, batches, model_type="llama")
+    assert set(layer_scales[0]) == {"attn_input_scale", "q_output_scale", "k_output_scale", "v_output_scale", "out_input_scale",
+                                    "gate_input_scale", "down_input_scale"}
+    qc = {"qkv": "per-tensor", "out": "per-token", "fc1": "per-tensor", "fc2": "per-token", "type": "int8"}
+    ln0 = model.model.layers[0].input_layernorm.weight.detach().clone()
+    assert quantize_decoder_layers(model, layer_scales, qc) == 2
+    layer0 = model.model.layers[0]
+    torch.testing.assert_close(layer0.input_layernorm.weight.detach(), ln0 / layer_scales[0]["attn_input_scale"])
+    assert isinstance(layer0.self_attn.k_proj, W8A8BFP32OFP32Linear) and layer0.self_attn.k_proj.weight.shape == (32, 64)
+    assert isinstance(layer0.mlp.down_proj, W8A8BFP32OFP32LinearWithQuantScale) and layer0.mlp.down_proj.act_quant == "per-token"
+    assert not hasattr(layer0.mlp.down_proj, "quant_scale")  # per-token modules carry no static input scale (linear.py:252-256)
+    assert isinstance(model.lm_head, nn.Linear)  # not quantized, as in the reference
+    out = save_quantized(model, tmp_path / "llama-smoothquant-int8", qc)
+    state, cfg2 = load_quantized(out)
+    assert cfg2 == qc
+    assert state["model.layers.1.self_attn.o_proj.weight"].dtype == torch.int8
+    assert state["model.layers.1.mlp.gate_proj.dequant_scale"].dim() == 0
+    assert "model.layers.0.self_attn.o_proj.quant_scale" not in state and "model.embed_tokens.weight" in state
