@@ -258,7 +258,10 @@ def _order_after_previous_launch(dev: torch.device, cur) -> None:
 def _stream(dev: torch.device) -> int:
     cur = torch.cuda.current_stream(dev)
     if _STREAM_GUARD:
-        _order_after_previous_launch(dev, cur)
+        try:
+            _order_after_previous_launch(dev, cur)
+        except Exception:  # noqa: BLE001 - bookkeeping must never be the reason a launch fails
+            pass
     return cur.cuda_stream
 
 
