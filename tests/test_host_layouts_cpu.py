@@ -111,3 +111,44 @@ def test_route_tokens_properties_hypothesis():
         assert torch.equal(real, torch.sort(real)[0])  # segments ordered by expert
 
     check()
+
+
+def _u8(t):
+    return t.view(torch.uint8) if t.dtype == torch.float8_e4m3fn else t
+
+
+def test_tensor_parallel_shards_of_the_fused_projections_cpu():
+    """build-time layout of the tensor-parallel stack (BASELINE configs 4 / 5), INT8 and FP8: every rank draws the same
+    seeded full-size weights, keeps its Megatron shard of each projection and THEN fuses q|k|v / gate|up — so a rank's fused
+    weight must be the concatenation of the r-th column shard of q, k, v (gate, up) of the unsharded model, its per-column
+    scales must be the unsharded ones (per-tensor weight scales are shared by all shards), and the row-parallel
+    projections must hold the r-th slice of K."""
+    world = 2
+    cfg = harness.TINY_GQA
+    for qc in ({}, {"type": "fp8", "qkv": "per-token", "out": "per-token", "fc1": "per-token", "fc2": "per-token"}):
+        full = harness.QuantDecoder(cfg, qc, device="cpu", seed=7, fuse_projections=True).layers[0]
+        q_n, k_n, v_n = full.qkv_sizes
+        I = cfg.intermediate
+        fw, gw = _u8(full.qkv_proj.weight), _u8(full.gate_up_proj.weight)
+        for r in range(world):
+            shard = harness.QuantDecoder(cfg, qc, device="cpu", seed=7, fuse_projections=True, tp=(r, world)).layers[0]
+            assert shard.qkv_sizes == [q_n // world, k_n // world, v_n // world]
+            want = torch.cat([fw[r * q_n // world:(r + 1) * q_n // world],
+                              fw[q_n + r * k_n // world:q_n + (r + 1) * k_n // world],
+                              fw[q_n + k_n + r * v_n // world:q_n + k_n + (r + 1) * v_n // world]])
+            assert torch.equal(_u8(shard.qkv_proj.weight), want)
+            want_gu = torch.cat([gw[r * I // world:(r + 1) * I // world], gw[I + r * I // world:I + (r + 1) * I // world]])
+            assert torch.equal(_u8(shard.gate_up_proj.weight), want_gu)
+            if qc:  # FP8: one weight scale per output column
+                fcs, scs = full.qkv_proj.col_scale, shard.qkv_proj.col_scale
+                assert scs.shape == (sum(shard.qkv_sizes),)
+                assert torch.equal(scs[:q_n // world], fcs[:q_n // world]) and torch.equal(scs[-1:], fcs[-1:])
+                assert torch.equal(shard.gate_up_proj.col_scale[:1], full.gate_up_proj.col_scale[:1])
+                assert float(shard.o_proj.weight_scale) == float(full.o_proj.weight_scale)
+            else:   # INT8: the three (two) dequant scalars of the fused-W_pack module
+                for name in full.qkv_proj._scale_names:
+                    assert float(getattr(shard.qkv_proj, name)) == float(getattr(full.qkv_proj, name))
+                assert float(shard.down_proj.dequant_scale) == float(full.down_proj.dequant_scale)
+            H = cfg.hidden
+            assert torch.equal(_u8(shard.o_proj.weight), _u8(full.o_proj.weight)[:, r * H // world:(r + 1) * H // world])
+            assert torch.equal(_u8(shard.down_proj.weight), _u8(full.down_proj.weight)[:, r * I // world:(r + 1) * I // world])
